@@ -1,0 +1,169 @@
+/*
+ * prl.h -- C ABI of the B200 batched physics environment.
+ *
+ * This is the drop-in boundary for the reference's one data-parallel hot path: stepping many
+ * independent `Environment`s through `Environment::step(Move)` and the genetic algorithm that
+ * drives them. The reference (a Rust crate) has no FFI of its own; each entry point below names
+ * the reference interface it replaces (file:line into the reference repo). A Rust `extern "C"`
+ * block binding these symbols is shown in INTEGRATION.md and rust/src/ffi.rs.
+ *
+ * Conventions
+ *  - every function returns PRL_OK (0) or a negative prl_status; prl_last_error() returns a
+ *    thread-local, NUL-terminated description of the last failure on the calling thread;
+ *  - handles are opaque, caller-owned and freed with the matching *_destroy;
+ *  - a batch / GA handle is bound to one CUDA device and one stream; it may be used from any
+ *    host thread (Algorithm::train runs off the main thread, train.rs:80) but by one thread at
+ *    a time;
+ *  - buffer arguments documented "host or device" are classified with
+ *    cudaPointerGetAttributes; host buffers are staged through the handle's stream and the
+ *    call returns after the data has arrived (device buffers: the call is asynchronous on the
+ *    handle's stream);
+ *  - a Move is one byte: bit0 = left, bit1 = right, bit2 = up (common.rs:351-356);
+ *  - there is NO CPU fallback: every compute entry point fails with PRL_ERR_CUDA when no
+ *    sm_100 device is usable.
+ */
+#ifndef PRL_H
+#define PRL_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PRL_ABI_VERSION 1
+
+typedef enum {
+    PRL_OK = 0,
+    PRL_ERR_INVALID = -1,   /* bad argument */
+    PRL_ERR_PARSE = -2,     /* World JSON does not match the serde schema */
+    PRL_ERR_CAPACITY = -3,  /* world exceeds the compiled limits (see prl_limits) */
+    PRL_ERR_NO_GOAL = -4,   /* distance_to_goals() on a goal-less world (reference: None / unwrap panic) */
+    PRL_ERR_CUDA = -5,      /* CUDA runtime failure, or no usable device */
+    PRL_ERR_OVERFLOW = -6   /* an environment needed more simultaneous contact manifolds than PRL_MAX_CONTACTS */
+} prl_status;
+
+#define PRL_MOVE_LEFT 1u
+#define PRL_MOVE_RIGHT 2u
+#define PRL_MOVE_UP 4u
+
+/* compiled limits */
+#define PRL_MAX_DYNAMIC 4     /* pushable blocks per world */
+#define PRL_MAX_BLOCKS 128    /* fixed + pushable blocks per world */
+#define PRL_MAX_PAIRS 128     /* candidate collider pairs per world */
+#define PRL_MAX_GOALS 16
+#define PRL_MAX_CONTACTS 16   /* simultaneous manifolds with solver contacts per environment */
+
+/* One `ObjectAndTransform` (common.rs:26-31). kind: 0 = WorldObject::Block{fixed:true},
+ * 1 = Block{fixed:false}, 2 = Goal (common.rs:46-49). */
+typedef struct {
+    float position[3];
+    float scale[2];
+    float rotation;
+    int32_t kind;
+} prl_object;
+
+typedef struct prl_world prl_world;
+typedef struct prl_batch prl_batch;
+typedef struct prl_ga prl_ga;
+
+const char* prl_last_error(void);
+int32_t prl_abi_version(void);
+/* number of CUDA devices visible to the library (0 when none / no driver) */
+int32_t prl_device_count(void);
+
+/* ------------------------------------------------------------------ World (common.rs:19-49) */
+/* `World { player_position, objects }` */
+int prl_world_create(const float player_position[2], const prl_object* objs, int32_t n_objects,
+                     prl_world** out);
+/* serde_json::from_str::<World> (editor.rs:916-936): externally tagged enum
+ * {"Block":{"fixed":bool}} | "Goal" */
+int prl_world_from_json(const char* utf8, size_t len, prl_world** out);
+/* serde_json::to_string(&World) (editor.rs:938-962). Writes at most cap bytes (incl. NUL) and
+ * always sets *needed to the size required. */
+int prl_world_to_json(const prl_world*, char* buf, size_t cap, size_t* needed);
+int32_t prl_world_num_objects(const prl_world*);
+int prl_world_get_object(const prl_world*, int32_t index, prl_object* out);
+int prl_world_player_position(const prl_world*, float out[2]);
+/* scene sizes after Environment::from_world (common.rs:162-172): bodies = 1 + pushable blocks,
+ * colliders = 1 + blocks */
+int prl_world_counts(const prl_world*, int32_t* n_bodies, int32_t* n_colliders, int32_t* n_goals,
+                     int32_t* n_pairs);
+/* from_world's Vec<Option<RigidBodyHandle>> (common.rs:162-172): body index of object `index`
+ * (>= 1), or -1 for None */
+int32_t prl_world_object_body(const prl_world*, int32_t index);
+void prl_world_destroy(prl_world*);
+
+/* ------------------------------------------------------------------ BatchedEnvironment */
+/* n_envs x Environment::from_world(world) (common.rs:162-172) on `device`. `stream` is a
+ * cudaStream_t (NULL = the legacy default stream). */
+int prl_batch_create(const prl_world*, int64_t n_envs, int32_t device, void* stream, prl_batch** out);
+void prl_batch_destroy(prl_batch*);
+int64_t prl_batch_num_envs(const prl_batch*);
+int32_t prl_batch_num_bodies(const prl_batch*);
+/* every environment back to its from_world state */
+int prl_batch_reset(prl_batch*);
+/* Environment::step (common.rs:215-340) for every environment; moves: n_envs bytes, host or device */
+int prl_batch_step(prl_batch*, const uint8_t* moves);
+/* the same Move for every environment, n_steps times (README.md:105-114 loop body) */
+int prl_batch_step_uniform(prl_batch*, uint32_t move, int32_t n_steps);
+/* Environment::distance_to_goals (common.rs:175-195), editor pixels; out: n_envs floats, host or device */
+int prl_batch_distance_to_goals(prl_batch*, float* out);
+/* Environment::won (common.rs:197-199); out: n_envs bytes (0/1), host or device */
+int prl_batch_won(prl_batch*, uint8_t* out);
+/* Observation, the batched form of rigid_body_set()/player_handle() (common.rs:201-211) as the
+ * viewers use them (train.rs:146-157, game.rs:134-145). Bodies in from_world handle order
+ * (0 = player). out: n x n_bodies x 9 floats, host only:
+ * x, y, cos, sin, vx, vy, angvel, sleep_timer, sleeping(0/1) */
+int prl_batch_get_state(prl_batch*, int64_t env0, int64_t n, float* out);
+/* overwrite body state (same layout; host only). Contact manifolds are kept. */
+int prl_batch_set_state(prl_batch*, int64_t env0, int64_t n, const float* in);
+/* GA fitness rollout (main.rs:44-70) for every environment, from the from_world state:
+ * genomes = n_envs x genome_len Moves (row per agent); the tail of
+ * number_of_steps % repeat_move default Moves is run as the reference does. early_exit = 1
+ * reproduces break-on-win; 0 always runs every step (throughput runs).
+ * out_score: min distance_to_goals over the rollout; out_step_of_win: 1-based step at which
+ * won() first became true, or -1. All buffers host or device; outputs may be NULL. */
+int prl_batch_rollout(prl_batch*, const uint8_t* genomes, int32_t genome_len, int32_t repeat_move,
+                      int32_t number_of_steps, int32_t early_exit, float* out_score,
+                      int32_t* out_step_of_win);
+/* wait for the handle's stream; returns PRL_ERR_OVERFLOW if any environment exceeded
+ * PRL_MAX_CONTACTS since the last reset */
+int prl_batch_sync(prl_batch*);
+/* kernels launched by this handle so far */
+int64_t prl_batch_launch_count(const prl_batch*);
+
+/* ------------------------------------------------------------------ Genetic algorithm (main.rs:18-163) */
+typedef struct {
+    int32_t number_of_steps;   /* main.rs:22, default 1000 */
+    int64_t number_of_agents;  /* main.rs:23, default 1000; GLOBAL population over all ranks */
+    int32_t repeat_move;       /* main.rs:24, default 20 */
+    float mutation_rate;       /* main.rs:25, default 0.1 */
+    int32_t keep_best;         /* main.rs:26, default false */
+    uint64_t seed;             /* the reference uses thread_rng (main.rs:42); here a Philox key */
+} prl_ga_config;
+
+/* Population slice [rank*N/n_ranks, (rank+1)*N/n_ranks) lives on `device`. */
+int prl_ga_create(const prl_world*, const prl_ga_config*, int32_t device, void* stream,
+                  int32_t rank, int32_t n_ranks, prl_ga** out);
+void prl_ga_destroy(prl_ga*);
+/* main.rs:72-84: random genomes for the local slice and their scores */
+int prl_ga_init(prl_ga*);
+/* Device buffers for the per-generation exchange (ncclAllGather by the host when n_ranks > 1):
+ * local_*: this rank's slice; global_*: all agents. With n_ranks == 1 local aliases global. */
+int prl_ga_buffers(prl_ga*, float** local_scores, uint8_t** local_genomes, float** global_scores,
+                   uint8_t** global_genomes, int64_t* local_count, int64_t* local_offset,
+                   int32_t* genome_len);
+/* main.rs:87-124: (best score, best genome) of the current global generation; first minimum
+ * wins ties. best_genome: genome_len bytes, host. */
+int prl_ga_best(prl_ga*, float* best_score, uint8_t* best_genome, int64_t* best_index);
+/* main.rs:126-160 for the local slice: elitism, weighted 2-parent choice, crossover, mutation,
+ * then scores the children. Reads the global buffers (which the host has all-gathered). */
+int prl_ga_next_generation(prl_ga*);
+int64_t prl_ga_generation(const prl_ga*);
+int64_t prl_ga_launch_count(const prl_ga*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PRL_H */
