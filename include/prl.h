@@ -116,8 +116,6 @@ int prl_batch_won(prl_batch*, uint8_t* out);
  * (0 = player). out: n x n_bodies x 9 floats, host only:
  * x, y, cos, sin, vx, vy, angvel, sleep_timer, sleeping(0/1) */
 int prl_batch_get_state(prl_batch*, int64_t env0, int64_t n, float* out);
-/* overwrite body state (same layout; host only). Contact manifolds are kept. */
-int prl_batch_set_state(prl_batch*, int64_t env0, int64_t n, const float* in);
 /* GA fitness rollout (main.rs:44-70) for every environment, from the from_world state:
  * genomes = n_envs x genome_len Moves (row per agent); the tail of
  * number_of_steps % repeat_move default Moves is run as the reference does. early_exit = 1
@@ -127,11 +125,17 @@ int prl_batch_set_state(prl_batch*, int64_t env0, int64_t n, const float* in);
 int prl_batch_rollout(prl_batch*, const uint8_t* genomes, int32_t genome_len, int32_t repeat_move,
                       int32_t number_of_steps, int32_t early_exit, float* out_score,
                       int32_t* out_step_of_win);
-/* wait for the handle's stream; returns PRL_ERR_OVERFLOW if any environment exceeded
- * PRL_MAX_CONTACTS since the last reset */
+/* Per environment since the last reset / rollout start: running minimum of distance_to_goals
+ * (the GA's score, main.rs:50), 1-based step at which won() first became true (-1: never) and
+ * the number of steps taken. Host or device buffers; any may be NULL. Synchronises. */
+int prl_batch_rollout_info(prl_batch*, float* out_score, int32_t* out_step_of_win, int32_t* out_steps);
+/* wait for the handle's stream; returns PRL_ERR_OVERFLOW if any environment needed more than
+ * PRL_MAX_CONTACTS simultaneous contact manifolds since the last reset */
 int prl_batch_sync(prl_batch*);
 /* kernels launched by this handle so far */
 int64_t prl_batch_launch_count(const prl_batch*);
+/* bytes of HBM holding the batch's state arrays */
+int64_t prl_batch_state_bytes(const prl_batch*);
 
 /* ------------------------------------------------------------------ Genetic algorithm (main.rs:18-163) */
 typedef struct {
@@ -155,13 +159,18 @@ int prl_ga_buffers(prl_ga*, float** local_scores, uint8_t** local_genomes, float
                    uint8_t** global_genomes, int64_t* local_count, int64_t* local_offset,
                    int32_t* genome_len);
 /* main.rs:87-124: (best score, best genome) of the current global generation; first minimum
- * wins ties. best_genome: genome_len bytes, host. */
+ * wins ties. best_genome: genome_len bytes, host or device; outputs may be NULL. With
+ * n_ranks == 1 the local slice is first copied into the global buffers (a one-rank all-gather);
+ * with n_ranks > 1 the host must have all-gathered them (prl_ga_buffers). */
 int prl_ga_best(prl_ga*, float* best_score, uint8_t* best_genome, int64_t* best_index);
 /* main.rs:126-160 for the local slice: elitism, weighted 2-parent choice, crossover, mutation,
  * then scores the children. Reads the global buffers (which the host has all-gathered). */
 int prl_ga_next_generation(prl_ga*);
 int64_t prl_ga_generation(const prl_ga*);
 int64_t prl_ga_launch_count(const prl_ga*);
+/* environment steps executed by the local slice's most recent scoring pass (early exit on win
+ * makes this less than n_local * number_of_steps); -1 on CUDA failure */
+int64_t prl_ga_env_steps(prl_ga*);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,338 @@
+// prl_api.cu -- the C ABI of include/prl.h over the batch kernels. No CPU fallback: every compute
+// entry point needs a CUDA device and fails with PRL_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "prl_host.h"
+#include "prl_batch.h"
+#include "prl_kernels.cuh"
+
+namespace prl {
+const char* last_error();
+}
+using namespace prl;
+
+
+
+namespace {
+
+
+bool is_device_ptr(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_stage(void** buf, size_t* cap, size_t bytes) {
+    if (*cap >= bytes) return PRL_OK;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+    CUDA_TRY(cudaMalloc(buf, bytes));
+    *cap = bytes;
+    return PRL_OK;
+}
+
+inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+// kernels are instantiated for 1 body (no pushable block), 2 bodies and the compiled maximum
+template <typename F1, typename F2, typename F5>
+void dispatch_bodies(int nb, F1 f1, F2 f2, F5 f5) {
+    if (nb == 1) f1();
+    else if (nb == 2) f2();
+    else f5();
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* prl_last_error(void) { return prl::last_error(); }
+int32_t prl_abi_version(void) { return PRL_ABI_VERSION; }
+int32_t prl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------------------- World
+int prl_world_create(const float player_position[2], const prl_object* objs, int32_t n_objects, prl_world** out) {
+    if (!player_position || !out || n_objects < 0 || (n_objects > 0 && !objs)) { set_error("prl_world_create: null argument"); return PRL_ERR_INVALID; }
+    prl_world* w = new (std::nothrow) prl_world();
+    if (!w) { set_error("out of memory"); return PRL_ERR_INVALID; }
+    w->player_position[0] = player_position[0];
+    w->player_position[1] = player_position[1];
+    w->objects.assign(objs, objs + n_objects);
+    int rc = build_dev_world(w);
+    if (rc != PRL_OK) { delete w; return rc; }
+    *out = w;
+    return PRL_OK;
+}
+
+int prl_world_from_json(const char* utf8, size_t len, prl_world** out) {
+    if (!utf8 || !out) { set_error("prl_world_from_json: null argument"); return PRL_ERR_INVALID; }
+    prl_world* w = new (std::nothrow) prl_world();
+    if (!w) { set_error("out of memory"); return PRL_ERR_INVALID; }
+    int rc = parse_world_json(utf8, len, w);
+    if (rc == PRL_OK) rc = build_dev_world(w);
+    if (rc != PRL_OK) { delete w; return rc; }
+    *out = w;
+    return PRL_OK;
+}
+
+int prl_world_to_json(const prl_world* w, char* buf, size_t cap, size_t* needed) {
+    if (!w) { set_error("prl_world_to_json: null world"); return PRL_ERR_INVALID; }
+    std::string s = world_to_json(w);
+    if (needed) *needed = s.size() + 1;
+    if (buf && cap > 0) {
+        size_t k = s.size() < cap - 1 ? s.size() : cap - 1;
+        memcpy(buf, s.data(), k);
+        buf[k] = 0;
+    }
+    return PRL_OK;
+}
+
+int32_t prl_world_num_objects(const prl_world* w) { return w ? (int32_t)w->objects.size() : 0; }
+int prl_world_get_object(const prl_world* w, int32_t index, prl_object* out) {
+    if (!w || !out || index < 0 || index >= (int32_t)w->objects.size()) { set_error("prl_world_get_object: bad index"); return PRL_ERR_INVALID; }
+    *out = w->objects[index];
+    return PRL_OK;
+}
+int prl_world_player_position(const prl_world* w, float out[2]) {
+    if (!w || !out) { set_error("prl_world_player_position: null argument"); return PRL_ERR_INVALID; }
+    out[0] = w->player_position[0];
+    out[1] = w->player_position[1];
+    return PRL_OK;
+}
+int prl_world_counts(const prl_world* w, int32_t* n_bodies, int32_t* n_colliders, int32_t* n_goals, int32_t* n_pairs) {
+    if (!w) { set_error("prl_world_counts: null world"); return PRL_ERR_INVALID; }
+    if (n_bodies) *n_bodies = w->dev.n_bodies;
+    if (n_colliders) *n_colliders = w->dev.n_colliders;
+    if (n_goals) *n_goals = w->dev.n_goals;
+    if (n_pairs) *n_pairs = w->dev.n_pairs;
+    return PRL_OK;
+}
+int32_t prl_world_object_body(const prl_world* w, int32_t index) {
+    if (!w || index < 0 || index >= (int32_t)w->object_body.size()) return -1;
+    return w->object_body[index];
+}
+void prl_world_destroy(prl_world* w) { delete w; }
+
+// ------------------------------------------------------------------------------- Batch
+int prl_batch_create(const prl_world* w, int64_t n_envs, int32_t device, void* stream, prl_batch** out) {
+    if (!w || !out || n_envs <= 0) { set_error("prl_batch_create: bad argument"); return PRL_ERR_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device is usable; this library has no CPU path");
+        return PRL_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { set_error("device %d out of range (%d visible)", device, ndev); return PRL_ERR_INVALID; }
+    DeviceGuard g(device);
+    prl_batch* b = new (std::nothrow) prl_batch();
+    if (!b) { set_error("out of memory"); return PRL_ERR_INVALID; }
+    b->world_src = w;
+    b->host_world = w->dev;
+    b->n = n_envs;
+    b->device = device;
+    b->stream = (cudaStream_t)stream;
+    b->words = state_words(w->dev.n_bodies, w->dev.n_slots);
+    cudaError_t e1 = cudaMalloc(&b->dev_world, sizeof(DevWorld));
+    cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&b->state, (size_t)b->words * (size_t)n_envs * 4u) : e1;
+    if (e2 != cudaSuccess) {
+        set_error("cudaMalloc of %d state words x %lld environments failed: %s", b->words, (long long)n_envs, cudaGetErrorString(e2));
+        if (b->dev_world) cudaFree(b->dev_world);
+        delete b;
+        return PRL_ERR_CUDA;
+    }
+    cudaError_t e3 = cudaMemcpyAsync(b->dev_world, &b->host_world, sizeof(DevWorld), cudaMemcpyHostToDevice, b->stream);
+    if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(b->stream);
+    if (e3 != cudaSuccess) {
+        set_error("uploading the world tables failed: %s", cudaGetErrorString(e3));
+        cudaFree(b->dev_world); cudaFree(b->state); delete b;
+        return PRL_ERR_CUDA;
+    }
+    int rc = prl_batch_reset(b);
+    if (rc != PRL_OK) { prl_batch_destroy(b); return rc; }
+    *out = b;
+    return PRL_OK;
+}
+
+void prl_batch_destroy(prl_batch* b) {
+    if (!b) return;
+    DeviceGuard g(b->device);
+    cudaStreamSynchronize(b->stream);
+    if (b->dev_world) cudaFree(b->dev_world);
+    if (b->state) cudaFree(b->state);
+    if (b->stage) cudaFree(b->stage);
+    if (b->stage2) cudaFree(b->stage2);
+    delete b;
+}
+
+int64_t prl_batch_num_envs(const prl_batch* b) { return b ? b->n : 0; }
+int32_t prl_batch_num_bodies(const prl_batch* b) { return b ? b->host_world.n_bodies : 0; }
+int64_t prl_batch_launch_count(const prl_batch* b) { return b ? b->launches : 0; }
+int64_t prl_batch_state_bytes(const prl_batch* b) { return b ? (int64_t)b->words * b->n * 4 : 0; }
+
+int prl_batch_reset(prl_batch* b) {
+    if (!b) { set_error("prl_batch_reset: null batch"); return PRL_ERR_INVALID; }
+    DeviceGuard g(b->device);
+    reset_kernel<<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n);
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    return PRL_OK;
+}
+
+static int launch_step(prl_batch* b, const uint8_t* dev_moves, uint32_t uniform, int n_steps) {
+    const int nb = b->host_world.n_bodies;
+    dispatch_bodies(
+        nb,
+        [&] { step_kernel<1><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dev_moves, uniform, n_steps); },
+        [&] { step_kernel<2><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dev_moves, uniform, n_steps); },
+        [&] { step_kernel<MAXB><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dev_moves, uniform, n_steps); });
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    return PRL_OK;
+}
+
+int prl_batch_step(prl_batch* b, const uint8_t* moves) {
+    if (!b || !moves) { set_error("prl_batch_step: null argument"); return PRL_ERR_INVALID; }
+    DeviceGuard g(b->device);
+    const uint8_t* dm = moves;
+    if (!is_device_ptr(moves)) {
+        int rc = ensure_stage(&b->stage, &b->stage_bytes, (size_t)b->n);
+        if (rc != PRL_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->stage, moves, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
+        // the caller may reuse `moves` as soon as we return
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        dm = (const uint8_t*)b->stage;
+    }
+    return launch_step(b, dm, 0, 1);
+}
+
+int prl_batch_step_uniform(prl_batch* b, uint32_t move, int32_t n_steps) {
+    if (!b || n_steps < 0) { set_error("prl_batch_step_uniform: bad argument"); return PRL_ERR_INVALID; }
+    if (n_steps == 0) return PRL_OK;
+    DeviceGuard g(b->device);
+    return launch_step(b, nullptr, move, n_steps);
+}
+
+static int observe(prl_batch* b, float* out_dist, uint8_t* out_won) {
+    DeviceGuard g(b->device);
+    void* host_out = nullptr;
+    size_t bytes = 0;
+    float* dd = out_dist;
+    uint8_t* dw = out_won;
+    if (out_dist && !is_device_ptr(out_dist)) {
+        bytes = (size_t)b->n * 4;
+        int rc = ensure_stage(&b->stage2, &b->stage2_bytes, bytes);
+        if (rc != PRL_OK) return rc;
+        dd = (float*)b->stage2;
+        host_out = out_dist;
+    }
+    if (out_won && !is_device_ptr(out_won)) {
+        bytes = (size_t)b->n;
+        int rc = ensure_stage(&b->stage2, &b->stage2_bytes, bytes);
+        if (rc != PRL_OK) return rc;
+        dw = (uint8_t*)b->stage2;
+        host_out = out_won;
+    }
+    observe_kernel<<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dd, dw);
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (host_out) {
+        CUDA_TRY(cudaMemcpyAsync(host_out, b->stage2, bytes, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    return PRL_OK;
+}
+
+int prl_batch_distance_to_goals(prl_batch* b, float* out) {
+    if (!b || !out) { set_error("prl_batch_distance_to_goals: null argument"); return PRL_ERR_INVALID; }
+    if (b->host_world.n_goals == 0) { set_error("the world has no goal: distance_to_goals() is None"); return PRL_ERR_NO_GOAL; }
+    return observe(b, out, nullptr);
+}
+
+int prl_batch_won(prl_batch* b, uint8_t* out) {
+    if (!b || !out) { set_error("prl_batch_won: null argument"); return PRL_ERR_INVALID; }
+    return observe(b, nullptr, out);
+}
+
+int prl_batch_get_state(prl_batch* b, int64_t env0, int64_t cnt, float* out) {
+    if (!b || !out || env0 < 0 || cnt < 0 || env0 + cnt > b->n) { set_error("prl_batch_get_state: bad range"); return PRL_ERR_INVALID; }
+    if (cnt == 0) return PRL_OK;
+    DeviceGuard g(b->device);
+    const int nb = b->host_world.n_bodies;
+    size_t bytes = (size_t)cnt * nb * 9 * 4;
+    bool dev = is_device_ptr(out);
+    float* d = out;
+    if (!dev) {
+        int rc = ensure_stage(&b->stage2, &b->stage2_bytes, bytes);
+        if (rc != PRL_OK) return rc;
+        d = (float*)b->stage2;
+    }
+    gather_state_kernel<<<grid_for(cnt * nb), kBlock, 0, b->stream>>>(b->state, b->n, nb, env0, cnt, d);
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) {
+        CUDA_TRY(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    return PRL_OK;
+}
+
+int prl_batch_rollout_info(prl_batch* b, float* out_score, int32_t* out_step_of_win, int32_t* out_steps) {
+    if (!b) { set_error("prl_batch_rollout_info: null batch"); return PRL_ERR_INVALID; }
+    DeviceGuard g(b->device);
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (out_score) CUDA_TRY(cudaMemcpy(out_score, b->state + (size_t)F_SCORE * b->n, (size_t)b->n * 4, cudaMemcpyDefault));
+    if (out_step_of_win) CUDA_TRY(cudaMemcpy(out_step_of_win, b->state + (size_t)F_WIN_STEP * b->n, (size_t)b->n * 4, cudaMemcpyDefault));
+    if (out_steps) CUDA_TRY(cudaMemcpy(out_steps, b->state + (size_t)F_STEPS * b->n, (size_t)b->n * 4, cudaMemcpyDefault));
+    return PRL_OK;
+}
+
+int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, int32_t repeat_move, int32_t number_of_steps,
+                      int32_t early_exit, float* out_score, int32_t* out_step_of_win) {
+    if (!b || !genomes || genome_len < 0 || repeat_move < 1 || number_of_steps < 0) { set_error("prl_batch_rollout: bad argument"); return PRL_ERR_INVALID; }
+    if (b->host_world.n_goals == 0) { set_error("the world has no goal: the rollout's distance_to_goals().unwrap() would panic (main.rs:50)"); return PRL_ERR_NO_GOAL; }
+    DeviceGuard g(b->device);
+    const uint8_t* dg = genomes;
+    size_t gbytes = (size_t)b->n * (size_t)genome_len;
+    if (!is_device_ptr(genomes) && gbytes > 0) {
+        int rc = ensure_stage(&b->stage, &b->stage_bytes, gbytes);
+        if (rc != PRL_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->stage, genomes, gbytes, cudaMemcpyHostToDevice, b->stream));
+        dg = (const uint8_t*)b->stage;
+    }
+    bool score_host = out_score && !is_device_ptr(out_score);
+    bool win_host = out_step_of_win && !is_device_ptr(out_step_of_win);
+    float* ds = score_host ? nullptr : out_score;
+    int32_t* dw = win_host ? nullptr : out_step_of_win;
+    const int nb = b->host_world.n_bodies;
+    dispatch_bodies(
+        nb,
+        [&] { rollout_kernel<1><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw); },
+        [&] { rollout_kernel<2><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw); },
+        [&] { rollout_kernel<MAXB><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw); });
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    // host outputs come straight from the state arrays the kernel also fills
+    if (score_host) CUDA_TRY(cudaMemcpyAsync(out_score, b->state + (size_t)F_SCORE * b->n, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (win_host) CUDA_TRY(cudaMemcpyAsync(out_step_of_win, b->state + (size_t)F_WIN_STEP * b->n, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (score_host || win_host || dg != genomes) CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return PRL_OK;
+}
+
+int prl_batch_sync(prl_batch* b) {
+    if (!b) { set_error("prl_batch_sync: null batch"); return PRL_ERR_INVALID; }
+    DeviceGuard g(b->device);
+    CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return PRL_OK;
+}
+
+}  // extern "C"

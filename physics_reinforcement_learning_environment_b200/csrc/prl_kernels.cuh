@@ -1,0 +1,238 @@
+// prl_kernels.cuh -- the batch kernels: one thread per environment, the world's static tables in
+// shared memory, the environment's state in registers for the whole launch.
+//
+//   reset_kernel     n x Environment::from_world (reference src/common.rs:162-172)
+//   step_kernel      Environment::step (common.rs:215-340) for every environment, n_steps times
+//                    (per-environment moves, or one move for all)
+//   rollout_kernel   the GA fitness rollout (src/main.rs:44-70) for every agent, from a fresh
+//                    from_world state, whole horizon in one launch
+//
+// HBM layout: structure of arrays, word(f, env) = state[f * n + env] (prl_world.h), so a warp's
+// loads and stores of one field are one coalesced 128-byte transaction.
+#pragma once
+#include "prl_device.cuh"
+
+namespace prl {
+
+constexpr int kBlock = 128;
+
+__device__ __forceinline__ void stage_world(DevWorld* dst, const DevWorld* __restrict__ src) {
+    static_assert(sizeof(DevWorld) % 16 == 0, "DevWorld is copied as 16-byte words");
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevWorld) / 16); i += blockDim.x) d[i] = s[i];
+    __syncthreads();
+}
+
+template <int NB>
+__device__ __forceinline__ void env_init(const DevWorld& W, Env<NB>& e) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        int c = b < W.n_bodies ? W.collider_of[b] : 0;
+        e.x[b] = W.cx[c]; e.y[b] = W.cy[c]; e.c[b] = W.cc[c]; e.s[b] = W.cs[c];
+        e.vx[b] = 0.0f; e.vy[b] = 0.0f; e.w[b] = 0.0f; e.timer[b] = 0.0f;
+    }
+    e.sleeping = 0;
+    e.flags = FLAG_FRESH;
+    e.order = 0;
+    e.count = 0;
+    e.used = 0;
+}
+
+template <int NB>
+__device__ __forceinline__ void env_load(const DevWorld& W, Env<NB>& e, const uint32_t* __restrict__ st, int64_t n, int64_t i) {
+    auto ld = [&](int f) { return __uint_as_float(st[(int64_t)f * n + i]); };
+    uint32_t fl = st[(int64_t)F_FLAGS * n + i];
+    e.sleeping = fl & 0xffu;
+    e.flags = fl & (FLAG_WON | FLAG_FRESH | FLAG_OVERFLOW);
+    e.count = (int)((fl >> 16) & 0xffu);
+    e.x[0] = ld(F_PLAYER); e.y[0] = ld(F_PLAYER + 1); e.c[0] = 1.0f; e.s[0] = 0.0f;
+    e.vx[0] = ld(F_PLAYER + 2); e.vy[0] = ld(F_PLAYER + 3); e.w[0] = 0.0f; e.timer[0] = ld(F_PLAYER + 4);
+#pragma unroll
+    for (int b = 1; b < NB; ++b) {
+        if (b < W.n_bodies) {
+            int f = F_DYN + 8 * (b - 1);
+            e.x[b] = ld(f); e.y[b] = ld(f + 1); e.c[b] = ld(f + 2); e.s[b] = ld(f + 3);
+            e.vx[b] = ld(f + 4); e.vy[b] = ld(f + 5); e.w[b] = ld(f + 6); e.timer[b] = ld(f + 7);
+        } else {
+            e.x[b] = e.y[b] = e.s[b] = e.vx[b] = e.vy[b] = e.w[b] = e.timer[b] = 0.0f;
+            e.c[b] = 1.0f;
+        }
+    }
+    // live manifolds are stored compacted in pair order: slot k = k-th manifold
+    int base = F_DYN + 8 * (W.n_bodies - 1);
+    e.order = 0xfedcba9876543210ull;
+    e.used = e.count >= 32 ? ~0u : ((1u << e.count) - 1u);
+    for (int k = 0; k < e.count; ++k) {
+        int f = base + MF_WORDS * k;
+        uint32_t h = st[(int64_t)f * n + i];
+        e.spair[k] = (int)(h & 0xffu);
+        e.snpts[k] = (int)(h >> 8);
+        for (int j = 0; j < 14; ++j) e.mf[k][j] = ld(f + 1 + j);
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void env_store(const DevWorld& W, const Env<NB>& e, uint32_t* __restrict__ st, int64_t n, int64_t i) {
+    auto sf = [&](int f, float v) { st[(int64_t)f * n + i] = __float_as_uint(v); };
+    int count = e.count < W.n_slots ? e.count : W.n_slots;
+    st[(int64_t)F_FLAGS * n + i] = (e.sleeping & 0xffu) | e.flags | ((uint32_t)count << 16);
+    sf(F_PLAYER, e.x[0]); sf(F_PLAYER + 1, e.y[0]); sf(F_PLAYER + 2, e.vx[0]); sf(F_PLAYER + 3, e.vy[0]);
+    sf(F_PLAYER + 4, e.timer[0]);
+#pragma unroll
+    for (int b = 1; b < NB; ++b) {
+        if (b < W.n_bodies) {
+            int f = F_DYN + 8 * (b - 1);
+            sf(f, e.x[b]); sf(f + 1, e.y[b]); sf(f + 2, e.c[b]); sf(f + 3, e.s[b]);
+            sf(f + 4, e.vx[b]); sf(f + 5, e.vy[b]); sf(f + 6, e.w[b]); sf(f + 7, e.timer[b]);
+        }
+    }
+    int base = F_DYN + 8 * (W.n_bodies - 1);
+    for (int k = 0; k < count; ++k) {
+        int slot = (int)((e.order >> (4 * k)) & 15u);
+        int f = base + MF_WORDS * k;
+        st[(int64_t)f * n + i] = (uint32_t)e.spair[slot] | ((uint32_t)e.snpts[slot] << 8);
+        for (int j = 0; j < 14; ++j) sf(f + 1 + j, e.mf[slot][j]);
+    }
+}
+
+// n x Environment::from_world (common.rs:162-172)
+__global__ void __launch_bounds__(kBlock) reset_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n) {
+    __shared__ DevWorld W;
+    stage_world(&W, dw);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto sf = [&](int f, float v) { st[(int64_t)f * n + i] = __float_as_uint(v); };
+    st[(int64_t)F_FLAGS * n + i] = FLAG_FRESH;
+    sf(F_SCORE, __int_as_float(0x7f800000));
+    st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)-1;
+    st[(int64_t)F_STEPS * n + i] = 0;
+    sf(F_PLAYER, W.cx[0]); sf(F_PLAYER + 1, W.cy[0]); sf(F_PLAYER + 2, 0.0f); sf(F_PLAYER + 3, 0.0f); sf(F_PLAYER + 4, 0.0f);
+    for (int b = 1; b < W.n_bodies; ++b) {
+        int c = W.collider_of[b], f = F_DYN + 8 * (b - 1);
+        sf(f, W.cx[c]); sf(f + 1, W.cy[c]); sf(f + 2, W.cc[c]); sf(f + 3, W.cs[c]);
+        sf(f + 4, 0.0f); sf(f + 5, 0.0f); sf(f + 6, 0.0f); sf(f + 7, 0.0f);
+    }
+}
+
+// Environment::step for every environment. moves != nullptr: one Move byte per environment and
+// n_steps == 1; else `uniform_move` for all, n_steps times. Also maintains the running minimum of
+// distance_to_goals, the step of the first win and the step counter.
+template <int NB>
+__global__ void __launch_bounds__(kBlock) step_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+                                                      const uint8_t* __restrict__ moves, uint32_t uniform_move, int n_steps) {
+    __shared__ DevWorld W;
+    stage_world(&W, dw);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Env<NB> e;
+    env_load(W, e, st, n, i);
+    float score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
+    int win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
+    int steps = (int)st[(int64_t)F_STEPS * n + i];
+    uint32_t mv = moves ? (moves[i] & 7u) : (uniform_move & 7u);
+    Stepper<NB, MAXC> sim(W, e);
+    for (int t = 0; t < n_steps; ++t) {
+        float d = sim.step(mv);
+        ++steps;
+        score = fminf(score, d);
+        if ((e.flags & FLAG_WON) && win_step < 0) win_step = steps;
+    }
+    env_store(W, e, st, n, i);
+    st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
+    st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
+    st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
+}
+
+// GA fitness rollout (main.rs:44-70) for every agent: fresh from_world state, genome g played
+// repeat_move times per gene, then number_of_steps % repeat_move default moves; score = min
+// distance_to_goals. early_exit reproduces the reference's break-on-win (including the tail's
+// extra step after a win); without it every step is executed (throughput runs).
+template <int NB>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+                                                         const uint8_t* __restrict__ genomes, int genome_len, int repeat_move,
+                                                         int number_of_steps, int early_exit,
+                                                         float* __restrict__ out_score, int32_t* __restrict__ out_win) {
+    __shared__ DevWorld W;
+    stage_world(&W, dw);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Env<NB> e;
+    env_init(W, e);
+    Stepper<NB, MAXC> sim(W, e);
+    float score = __int_as_float(0x7f800000);
+    int win_step = -1, steps = 0;
+    const uint8_t* genome = genomes + i * (int64_t)genome_len;
+    bool stop = false;
+    for (int g = 0; g < genome_len && !stop; ++g) {
+        uint32_t mv = genome[g] & 7u;
+        for (int r = 0; r < repeat_move; ++r) {
+            float d = sim.step(mv);
+            ++steps;
+            score = fminf(score, d);
+            bool won = (e.flags & FLAG_WON) != 0;
+            if (won && win_step < 0) win_step = steps;
+            if (won && early_exit) { stop = true; break; }
+        }
+    }
+    int tail = number_of_steps % repeat_move;
+    for (int r = 0; r < tail; ++r) {
+        float d = sim.step(0u);
+        ++steps;
+        score = fminf(score, d);
+        bool won = (e.flags & FLAG_WON) != 0;
+        if (won && win_step < 0) win_step = steps;
+        if (won && early_exit) break;
+    }
+    env_store(W, e, st, n, i);
+    st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
+    st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
+    st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
+    if (out_score) out_score[i] = score;
+    if (out_win) out_win[i] = win_step;
+}
+
+// Environment::distance_to_goals (common.rs:175-195) and Environment::won (common.rs:197-199)
+__global__ void __launch_bounds__(kBlock) observe_kernel(const DevWorld* __restrict__ dw, const uint32_t* __restrict__ st, int64_t n,
+                                                         float* __restrict__ out_dist, uint8_t* __restrict__ out_won) {
+    __shared__ DevWorld W;
+    stage_world(&W, dw);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (out_won) out_won[i] = (st[(int64_t)F_FLAGS * n + i] & FLAG_WON) ? 1 : 0;
+    if (out_dist) {
+        float px = __uint_as_float(st[(int64_t)F_PLAYER * n + i]), py = __uint_as_float(st[(int64_t)(F_PLAYER + 1) * n + i]);
+        float best = __int_as_float(0x7f800000);
+        for (int g = 0; g < W.n_goals; ++g) {
+            float dx0 = px - W.gx[g], dy0 = py - W.gy[g];
+            float dx = fmaxf(fabsf(dx0 * W.gxax[g] + dy0 * W.gxay[g]) - W.ghw[g], 0.0f);
+            float dy = fmaxf(fabsf(dx0 * W.gyax[g] + dy0 * W.gyay[g]) - W.ghh[g], 0.0f);
+            float dist = sqrtf(dx * dx + dy * dy) / W.scale;
+            best = g == 0 ? dist : fminf(best, dist);
+        }
+        out_dist[i] = best;
+    }
+}
+
+// Observation: bodies of environments [env0, env0+cnt) as cnt x n_bodies x 9 floats
+// (x, y, cos, sin, vx, vy, angvel, sleep timer, sleeping)
+__global__ void __launch_bounds__(kBlock) gather_state_kernel(const uint32_t* __restrict__ st, int64_t n, int n_bodies, int64_t env0,
+                                                              int64_t cnt, float* __restrict__ out) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cnt * n_bodies) return;
+    int64_t i = env0 + t / n_bodies;
+    int b = (int)(t % n_bodies);
+    auto ld = [&](int f) { return __uint_as_float(st[(int64_t)f * n + i]); };
+    float* o = out + t * 9;
+    uint32_t fl = st[(int64_t)F_FLAGS * n + i];
+    if (b == 0) {
+        o[0] = ld(F_PLAYER); o[1] = ld(F_PLAYER + 1); o[2] = 1.0f; o[3] = 0.0f;
+        o[4] = ld(F_PLAYER + 2); o[5] = ld(F_PLAYER + 3); o[6] = 0.0f; o[7] = ld(F_PLAYER + 4);
+    } else {
+        int f = F_DYN + 8 * (b - 1);
+        for (int j = 0; j < 8; ++j) o[j] = ld(f + j);
+    }
+    o[8] = (float)((fl >> b) & 1u);
+}
+
+}  // namespace prl

@@ -1,0 +1,343 @@
+// prl_world.cc -- `World` ingest (serde JSON schema, reference src/common.rs:19-49) and the host
+// side of `Environment::from_world` (common.rs:70-172): every level object becomes a row of the
+// static DevWorld tables the kernels stage in shared memory.
+//
+// All physics-space values are computed in f32 with the expression order of the reference and
+// of the crates it calls (rapier2d 0.17.2 builders, parry2d 0.13.4 mass properties); this file
+// must be compiled without FMA contraction (-ffp-contract=off).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <charconv>
+
+#include "prl_host.h"
+#include "prl_libm.h"
+
+namespace prl {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static inline float inv0(float x) { return x == 0.0f ? 0.0f : 1.0f / x; }
+
+// common.rs:7-9
+static const float kPlayerDepth = 20.0f, kPlayerRadius = 20.0f;
+static const float kScale = 0.25f / (2.0f * 20.0f);
+
+int build_dev_world(prl_world* w) {
+    DevWorld& d = w->dev;
+    memset(&d, 0, sizeof d);
+    const int n = (int)w->objects.size();
+    int nblocks = 0, ndyn = 0, ngoals = 0;
+    for (int i = 0; i < n; ++i) {
+        int k = w->objects[i].kind;
+        if (k == 2) ++ngoals;
+        else if (k == 0 || k == 1) { ++nblocks; if (k == 1) ++ndyn; }
+        else { set_error("object %d: kind %d is not 0 (fixed block), 1 (pushable block) or 2 (goal)", i, k); return PRL_ERR_INVALID; }
+    }
+    if (nblocks > PRL_MAX_BLOCKS) { set_error("world has %d blocks, limit PRL_MAX_BLOCKS=%d", nblocks, PRL_MAX_BLOCKS); return PRL_ERR_CAPACITY; }
+    if (ndyn > PRL_MAX_DYNAMIC) { set_error("world has %d pushable blocks, limit PRL_MAX_DYNAMIC=%d", ndyn, PRL_MAX_DYNAMIC); return PRL_ERR_CAPACITY; }
+    if (ngoals > PRL_MAX_GOALS) { set_error("world has %d goals, limit PRL_MAX_GOALS=%d", ngoals, PRL_MAX_GOALS); return PRL_ERR_CAPACITY; }
+    d.n_colliders = 1 + nblocks;
+    d.n_bodies = 1 + ndyn;
+    d.n_goals = ngoals;
+
+    // rapier IntegrationParameters::default() and its derived inv_dt / erp_inv_dt / cfm_factor
+    const float dt = 1.0f / 60.0f, erp = 0.8f, damping_ratio = 0.25f;
+    d.dt = dt;
+    d.inv_dt = 1.0f / dt;
+    d.erp_inv_dt = erp * d.inv_dt;
+    {
+        float a = 1.0f / erp - 1.0f;
+        float cfm_coeff = a * a / ((1.0f + a) * 4.0f * damping_ratio * damping_ratio);
+        d.cfm_factor = 1.0f / (1.0f + cfm_coeff);
+    }
+    d.prediction = 0.002f;
+    d.allowed_linear_error = 0.001f;
+    d.aabb_margin = d.prediction / 2.0f;
+    d.scale = kScale;
+
+    // Environment::new (common.rs:70-86): rotation-locked dynamic body + capsule_y collider
+    d.half_height = 0.5f * kPlayerDepth * kScale;
+    d.radius = kPlayerRadius * kScale;
+    d.lower_off = kPlayerDepth * kScale / 2.0f;  // common.rs:219
+    d.cx[0] = w->player_position[0] * kScale;
+    d.cy[0] = w->player_position[1] * kScale;
+    d.cc[0] = 1.0f;
+    d.cs[0] = 0.0f;
+    d.hx[0] = d.radius;
+    d.hy[0] = d.half_height;
+    d.body_of[0] = 0;
+    d.collider_of[0] = 0;
+    {
+        // parry MassProperties::from_capsule (2-D), density 1; rotations locked -> no angular part
+        float hh = (d.half_height - (-d.half_height)) / 2.0f;
+        float cyl = d.radius * hh * 4.0f;
+        float ball = 3.14159265358979323846f * d.radius * d.radius;
+        float mass = (cyl + ball) * 1.0f;
+        d.inv_mass[0] = inv0(mass);
+        d.inv_inertia_sqrt[0] = 0.0f;
+        d.ccd_thickness[0] = d.radius;
+    }
+
+    // add_object (common.rs:107-159)
+    w->object_body.assign(n, -1);
+    int ci = 1, bi = 1, gi = 0;
+    for (int i = 0; i < n; ++i) {
+        const prl_object& o = w->objects[i];
+        if (o.kind == 2) {
+            d.gx[gi] = o.position[0] * kScale;
+            d.gy[gi] = o.position[1] * kScale;
+            float gw = fabsf(o.scale[0]) * kScale, gh = fabsf(o.scale[1]) * kScale;
+            d.ghw[gi] = gw / 2.0f;
+            d.ghh[gi] = gh / 2.0f;
+            // glam Quat::from_rotation_z(rot) * Vec3::X / Vec3::Y, truncated (common.rs:183-184)
+            float s = sinf(o.rotation * 0.5f), c = cosf(o.rotation * 0.5f);
+            float k = c * c - ((0.0f * 0.0f + 0.0f * 0.0f) + s * s);
+            float w2 = c * 2.0f;
+            d.gxax[gi] = k + 0.0f + 0.0f;
+            d.gxay[gi] = 0.0f + 0.0f + s * w2;
+            d.gyax[gi] = 0.0f + 0.0f + (0.0f - s) * w2;
+            d.gyay[gi] = k + 0.0f + 0.0f;
+            ++gi;
+            continue;
+        }
+        d.hx[ci] = 0.5f * fabsf(o.scale[0]) * kScale;
+        d.hy[ci] = 0.5f * fabsf(o.scale[1]) * kScale;
+        d.cx[ci] = o.position[0] * kScale;
+        d.cy[ci] = o.position[1] * kScale;
+        d.cc[ci] = libm_cosf(o.rotation);
+        d.cs[ci] = libm_sinf(o.rotation);
+        if (o.kind == 0) {
+            d.body_of[ci] = -1;
+            // parry Cuboid::aabb, loosened by prediction / 2 per side (rapier broad phase)
+            float ac = fabsf(d.cc[ci]), as = fabsf(d.cs[ci]);
+            float wx = ac * d.hx[ci] + as * d.hy[ci], wy = as * d.hx[ci] + ac * d.hy[ci];
+            d.amnx[ci] = (d.cx[ci] - wx) - d.aabb_margin;
+            d.amny[ci] = (d.cy[ci] - wy) - d.aabb_margin;
+            d.amxx[ci] = (d.cx[ci] + wx) + d.aabb_margin;
+            d.amxy[ci] = (d.cy[ci] + wy) + d.aabb_margin;
+        } else {
+            // parry MassProperties::from_cuboid (2-D), density 1
+            float volume = d.hx[ci] * d.hy[ci] * 4.0f;
+            float ix = (d.hx[ci] * d.hx[ci]) / 3.0f, iy = (d.hy[ci] * d.hy[ci]) / 3.0f;
+            float mass = volume * 1.0f;
+            float inertia = (ix + iy) * mass;
+            d.inv_mass[bi] = inv0(mass);
+            d.inv_inertia_sqrt[bi] = inv0(sqrtf(inertia));
+            d.ccd_thickness[bi] = fminf(d.hx[ci], d.hy[ci]);
+            d.collider_of[bi] = ci;
+            d.body_of[ci] = (int8_t)bi;
+            w->object_body[i] = bi;
+            ++bi;
+        }
+        ++ci;
+    }
+    // gravity (0,-2) (common.rs:316): force = mass * gravity; velocity increment (force * inv_mass) * dt
+    for (int b = 0; b < d.n_bodies; ++b) {
+        float mass = inv0(d.inv_mass[b]);
+        float fx = 0.0f + (0.0f * mass) * 1.0f, fy = 0.0f + (-2.0f * mass) * 1.0f;
+        d.gdv_x[b] = 0.0f + (fx * d.inv_mass[b]) * dt;
+        d.gdv_y[b] = 0.0f + (fy * d.inv_mass[b]) * dt;
+    }
+    // candidate collider pairs in ascending (collider1, collider2) order; two parent-less
+    // colliders never collide
+    int np = 0, npp = 0;
+    for (int a = 0; a < d.n_colliders; ++a)
+        for (int b = a + 1; b < d.n_colliders; ++b) {
+            if (d.body_of[a] < 0 && d.body_of[b] < 0) continue;
+            if (np >= PRL_MAX_PAIRS) { set_error("world needs more than PRL_MAX_PAIRS=%d candidate collider pairs", PRL_MAX_PAIRS); return PRL_ERR_CAPACITY; }
+            d.pair_c1[np] = (uint8_t)a;
+            d.pair_c2[np] = (uint8_t)b;
+            if (a == 0) ++npp;
+            ++np;
+        }
+    d.n_pairs = np;
+    d.n_player_pairs = npp;
+    d.n_slots = np < MAXC ? np : MAXC;
+    return PRL_OK;
+}
+
+// ---------------------------------------------------------------------------- JSON
+namespace {
+struct Cur {
+    const char* p;
+    const char* e;
+    void ws() { while (p < e && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p; }
+    bool eat(char c) { ws(); if (p < e && *p == c) { ++p; return true; } return false; }
+    bool key(std::string* out) {
+        ws();
+        if (p >= e || *p != '"') return false;
+        ++p;
+        out->clear();
+        while (p < e && *p != '"') {
+            if (*p == '\\') return false;  // the schema's keys and tags contain no escapes
+            out->push_back(*p++);
+        }
+        if (p >= e) return false;
+        ++p;
+        return true;
+    }
+    bool num(float* out) {
+        ws();
+        const char* s = p;
+        if (p < e && *p == '-') ++p;
+        bool digits = false;
+        while (p < e && *p >= '0' && *p <= '9') { ++p; digits = true; }
+        if (p < e && *p == '.') { ++p; while (p < e && *p >= '0' && *p <= '9') { ++p; digits = true; } }
+        if (digits && p < e && (*p == 'e' || *p == 'E')) {
+            ++p;
+            if (p < e && (*p == '+' || *p == '-')) ++p;
+            while (p < e && *p >= '0' && *p <= '9') ++p;
+        }
+        if (!digits) return false;
+        std::string tmp(s, p);
+        *out = (float)strtod(tmp.c_str(), nullptr);  // serde_json: f64 parse, then `as f32`
+        return true;
+    }
+    bool boolean(bool* out) {
+        ws();
+        if (e - p >= 4 && !strncmp(p, "true", 4)) { p += 4; *out = true; return true; }
+        if (e - p >= 5 && !strncmp(p, "false", 5)) { p += 5; *out = false; return true; }
+        return false;
+    }
+    bool farray(float* out, int n) {
+        if (!eat('[')) return false;
+        for (int i = 0; i < n; ++i) {
+            if (i && !eat(',')) return false;
+            if (!num(&out[i])) return false;
+        }
+        return eat(']');
+    }
+};
+
+bool parse_object_tag(Cur& c, int* kind) {
+    c.ws();
+    std::string k;
+    if (c.p < c.e && *c.p == '"') {  // unit variant: "Goal"
+        if (!c.key(&k) || k != "Goal") return false;
+        *kind = 2;
+        return true;
+    }
+    // struct variant: {"Block":{"fixed":bool}}
+    if (!c.eat('{') || !c.key(&k) || k != "Block" || !c.eat(':') || !c.eat('{')) return false;
+    if (!c.key(&k) || k != "fixed" || !c.eat(':')) return false;
+    bool fixed;
+    if (!c.boolean(&fixed)) return false;
+    if (!c.eat('}') || !c.eat('}')) return false;
+    *kind = fixed ? 0 : 1;
+    return true;
+}
+
+bool parse_object(Cur& c, prl_object* o) {
+    if (!c.eat('{')) return false;
+    unsigned seen = 0;
+    bool first = true;
+    while (!c.eat('}')) {
+        if (!first && !c.eat(',')) return false;
+        first = false;
+        std::string k;
+        if (!c.key(&k) || !c.eat(':')) return false;
+        if (k == "object") { if (!parse_object_tag(c, &o->kind)) return false; seen |= 1; }
+        else if (k == "position") { if (!c.farray(o->position, 3)) return false; seen |= 2; }
+        else if (k == "scale") { if (!c.farray(o->scale, 2)) return false; seen |= 4; }
+        else if (k == "rotation") { if (!c.num(&o->rotation)) return false; seen |= 8; }
+        else return false;
+    }
+    return seen == 15;
+}
+}  // namespace
+
+int parse_world_json(const char* s, size_t len, prl_world* out) {
+    Cur c{s, s + len};
+    unsigned seen = 0;
+    bool first = true;
+    if (!c.eat('{')) goto bad;
+    while (!c.eat('}')) {
+        if (!first && !c.eat(',')) goto bad;
+        first = false;
+        std::string k;
+        if (!c.key(&k) || !c.eat(':')) goto bad;
+        if (k == "player_position") {
+            if (!c.farray(out->player_position, 2)) goto bad;
+            seen |= 1;
+        } else if (k == "objects") {
+            if (!c.eat('[')) goto bad;
+            out->objects.clear();
+            if (!c.eat(']')) {
+                for (;;) {
+                    prl_object o;
+                    memset(&o, 0, sizeof o);
+                    if (!parse_object(c, &o)) goto bad;
+                    out->objects.push_back(o);
+                    if (c.eat(',')) continue;
+                    if (c.eat(']')) break;
+                    goto bad;
+                }
+            }
+            seen |= 2;
+        } else {
+            goto bad;
+        }
+    }
+    c.ws();
+    if (c.p != c.e || seen != 3) goto bad;
+    return PRL_OK;
+bad:
+    set_error("World JSON does not match the serde schema of common.rs:19-49 near byte %ld", (long)(c.p - s));
+    return PRL_ERR_PARSE;
+}
+
+// serde_json prints f32 with ryu: shortest round-trip digits, always a '.0' on integers,
+// exponents as e-7 / e20
+static void put_f32(std::string& s, float v) {
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v);
+    std::string t(buf, r.ptr);
+    size_t ep = t.find('e');
+    if (ep != std::string::npos) {
+        std::string mant = t.substr(0, ep), ex = t.substr(ep + 1);
+        bool neg = !ex.empty() && ex[0] == '-';
+        if (!ex.empty() && (ex[0] == '-' || ex[0] == '+')) ex.erase(0, 1);
+        while (ex.size() > 1 && ex[0] == '0') ex.erase(0, 1);
+        t = mant + "e" + (neg ? "-" : "") + ex;
+    } else if (t.find('.') == std::string::npos && t.find("inf") == std::string::npos && t.find("nan") == std::string::npos) {
+        t += ".0";
+    }
+    s += t;
+}
+
+std::string world_to_json(const prl_world* w) {
+    std::string s = "{\"player_position\":[";
+    put_f32(s, w->player_position[0]);
+    s += ",";
+    put_f32(s, w->player_position[1]);
+    s += "],\"objects\":[";
+    for (size_t i = 0; i < w->objects.size(); ++i) {
+        const prl_object& o = w->objects[i];
+        if (i) s += ",";
+        s += "{\"object\":";
+        if (o.kind == 2) s += "\"Goal\"";
+        else s += o.kind == 0 ? "{\"Block\":{\"fixed\":true}}" : "{\"Block\":{\"fixed\":false}}";
+        s += ",\"position\":[";
+        put_f32(s, o.position[0]); s += ","; put_f32(s, o.position[1]); s += ","; put_f32(s, o.position[2]);
+        s += "],\"scale\":[";
+        put_f32(s, o.scale[0]); s += ","; put_f32(s, o.scale[1]);
+        s += "],\"rotation\":";
+        put_f32(s, o.rotation);
+        s += "}";
+    }
+    s += "]}";
+    return s;
+}
+
+}  // namespace prl

@@ -16,16 +16,18 @@ constexpr int MAXCOL = PRL_MAX_BLOCKS + 1;   // colliders: player + blocks
 constexpr int MAXB = PRL_MAX_DYNAMIC + 1;    // bodies: player + pushable blocks
 constexpr int MAXP = PRL_MAX_PAIRS;
 constexpr int MAXG = PRL_MAX_GOALS;
-constexpr int MAXC = PRL_MAX_CONTACTS;
-constexpr int MF_WORDS = 14;                 // manifold cache words per pair (see prl_device.cuh)
+constexpr int MAXC = PRL_MAX_CONTACTS;       // manifold slots per environment
+constexpr int MF_WORDS = 15;                 // HBM words per manifold slot (see prl_device.cuh)
 
-struct DevWorld {
+struct alignas(16) DevWorld {
     int32_t n_colliders, n_bodies, n_pairs, n_goals;
+    int32_t n_player_pairs;  // pairs whose collider1 is the player capsule come first
+    int32_t n_slots;         // manifold slots kept per environment in HBM = min(n_pairs, MAXC)
     // player capsule (common.rs:74-86) and glue constants (common.rs:216-220, 234-236)
     float radius, half_height, lower_off;
     // integration parameters (rapier IntegrationParameters::default, derived values)
     float dt, inv_dt, erp_inv_dt, cfm_factor, prediction, allowed_linear_error, aabb_margin;
-    float inv_scale_div;  // BEVY_TO_PHYSICS_SCALE (distance_to_goals divides by it, common.rs:193)
+    float scale;  // BEVY_TO_PHYSICS_SCALE (distance_to_goals divides by it, common.rs:192)
     // colliders in insertion order; 0 = player capsule (common.rs:86, 125, 140-144)
     float cx[MAXCOL], cy[MAXCOL], cc[MAXCOL], cs[MAXCOL];  // pose (initial pose for pushable blocks)
     float hx[MAXCOL], hy[MAXCOL];                          // cuboid half extents
@@ -33,7 +35,7 @@ struct DevWorld {
     int8_t body_of[MAXCOL];                                // -1: parent-less (fixed) collider
     // bodies in handle order; 0 = player
     float inv_mass[MAXB], inv_inertia_sqrt[MAXB], ccd_thickness[MAXB];
-    float gdv_x[MAXB], gdv_y[MAXB];                        // (force * inv_mass) * dt with force = mass * gravity
+    float gdv_x[MAXB], gdv_y[MAXB];                        // 0 + (force * inv_mass) * dt with force = mass * gravity
     int32_t collider_of[MAXB];
     // candidate pairs, ascending (collider1, collider2), fixed-fixed excluded
     uint8_t pair_c1[MAXP], pair_c2[MAXP];
@@ -41,5 +43,22 @@ struct DevWorld {
     float gx[MAXG], gy[MAXG], ghw[MAXG], ghh[MAXG];        // centre, width/2, height/2
     float gxax[MAXG], gxay[MAXG], gyax[MAXG], gyay[MAXG];  // Quat::from_rotation_z(rot) * X / Y, truncated
 };
+
+// ---- HBM state layout of a batch: structure of arrays, one 32-bit word per field per environment:
+// word(f, env) = state[f * n_envs + env]. Fields:
+//   F_FLAGS                          bits 0-7 sleeping mask (bit b = body b), bit 8 won, bit 9 fresh
+//                                    (no pipeline step taken yet), bit 10 manifold-slot overflow,
+//                                    bits 16-23 number of live manifold slots
+//   F_SCORE, F_WIN_STEP, F_STEPS     running min of distance_to_goals, 1-based step of the first
+//                                    won() (-1: none), steps since reset
+//   F_PLAYER .. +4                   x, y, vx, vy, sleep timer (rotations locked: cos=1, sin=0, w=0)
+//   F_DYN + 8*(b-1) .. +7            x, y, cos, sin, vx, vy, angvel, sleep timer of pushable block b
+//   slots                            n_slots x MF_WORDS: word 0 = pair | npts << 8, then local_n1,
+//                                    local_n2, 2 x (local_p1, local_p2, dist)
+enum { F_FLAGS = 0, F_SCORE = 1, F_WIN_STEP = 2, F_STEPS = 3, F_PLAYER = 4, F_DYN = 9 };
+constexpr uint32_t FLAG_WON = 1u << 8, FLAG_FRESH = 1u << 9, FLAG_OVERFLOW = 1u << 10;
+
+inline int state_slot_base(int n_bodies) { return F_DYN + 8 * (n_bodies - 1); }
+inline int state_words(int n_bodies, int n_slots) { return state_slot_base(n_bodies) + MF_WORDS * n_slots; }
 
 }  // namespace prl

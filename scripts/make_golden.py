@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/*.npz.
+
+The reference (Rust + rapier2d 0.17.2 from crates.io) cannot be built or run in this image and
+ships no golden vectors, so these fixtures are produced by the CPU ORACLE
+(oracle/prl_oracle.c) -- they pin the oracle and the CUDA path against regressions and against
+each other, not against rapier itself: PARITY UNPINNED. If real-rapier dumps ever become
+available, drop them in tests/golden/ in the same format (see tests/test_golden.py).
+
+Format, per world: genomes (16 x 50 uint8), repeat_move, number_of_steps, score (f32), step_of_win
+(i32), steps_run (i32) with the reference's early exit, and the full body trajectory of the first
+4 genomes without early exit: traj[g, step, body, 9].
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle.binding import OracleEnv  # noqa: E402
+
+
+def main():
+    out_dir = os.path.join(ROOT, "tests", "golden")
+    for name in ("right", "jump", "push"):
+        world = json.load(open(os.path.join(ROOT, "worlds", f"{name}.json")))
+        rng = np.random.Generator(np.random.Philox(0xB200))
+        genomes = rng.integers(0, 8, size=(16, 50), dtype=np.uint8)
+        genomes[:8] = np.arange(8, dtype=np.uint8)[:, None]  # the 8 constant moves of README.md:96-114
+        repeat, steps = 20, 1000
+        env = OracleEnv(world)
+        score = np.zeros(16, np.float32); win = np.zeros(16, np.int32); run = np.zeros(16, np.int32)
+        for i in range(16):
+            score[i], win[i], run[i] = env.rollout(genomes[i], repeat, steps, early_exit=True)
+        traj = np.zeros((4, steps, env.num_bodies, 9), np.float32)
+        for gi, g in enumerate((2, 6, 8, 9)):
+            env.reset()
+            for t in range(steps):
+                env.step(int(genomes[g][t // repeat]))
+                traj[gi, t] = env.state()
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), genomes=genomes, repeat_move=repeat,
+                            number_of_steps=steps, score=score, step_of_win=win, steps_run=run,
+                            traj_genomes=np.array((2, 6, 8, 9)), traj=traj[:, ::10].copy())
+        print(name, "scores", score[:8], "wins", win)
+
+
+if __name__ == "__main__":
+    main()

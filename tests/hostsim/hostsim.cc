@@ -1,0 +1,78 @@
+// hostsim.cc -- TEST INFRASTRUCTURE, never shipped: compiles the product's per-environment device
+// logic (csrc/prl_device.cuh) with g++ so the `-m "not gpu"` tests can run it, one environment at
+// a time, against the oracle on a machine without a GPU. The product library (libprl.so) does not
+// contain or call any of this; its only execution path is the CUDA kernels.
+#include <stdint.h>
+#include <string.h>
+
+#include "../../physics_reinforcement_learning_environment_b200/csrc/prl_device.cuh"
+#include "../../physics_reinforcement_learning_environment_b200/csrc/prl_host.h"
+
+using namespace prl;
+
+template <int NB>
+static void init_env(const DevWorld& W, Env<NB>& e) {
+    memset(&e, 0, sizeof e);
+    for (int b = 0; b < NB; ++b) {
+        int c = b < W.n_bodies ? W.collider_of[b] : 0;
+        e.x[b] = W.cx[c]; e.y[b] = W.cy[c]; e.c[b] = W.cc[c]; e.s[b] = W.cs[c];
+    }
+    e.flags = FLAG_FRESH;
+}
+
+template <int NB>
+static float rollout(const DevWorld& W, const uint8_t* genome, int genome_len, int repeat_move, int number_of_steps,
+                     int early_exit, float* traj, int* win_out, int* steps_out, int* overflow) {
+    static Env<NB> e;
+    init_env(W, e);
+    Stepper<NB, MAXC> sim(W, e);
+    float score = INFINITY;
+    int win = -1, steps = 0;
+    auto record = [&]() {
+        if (!traj) return;
+        for (int b = 0; b < W.n_bodies; ++b) {
+            float* o = traj + ((size_t)(steps - 1) * W.n_bodies + b) * 9;
+            o[0] = e.x[b]; o[1] = e.y[b]; o[2] = e.c[b]; o[3] = e.s[b]; o[4] = e.vx[b]; o[5] = e.vy[b];
+            o[6] = e.w[b]; o[7] = e.timer[b]; o[8] = (float)((e.sleeping >> b) & 1u);
+        }
+    };
+    bool stop = false;
+    for (int g = 0; g < genome_len && !stop; ++g) {
+        for (int r = 0; r < repeat_move; ++r) {
+            float d = sim.step(genome[g] & 7u);
+            ++steps;
+            record();
+            score = fminf(score, d);
+            bool won = (e.flags & FLAG_WON) != 0;
+            if (won && win < 0) win = steps;
+            if (won && early_exit) { stop = true; break; }
+        }
+    }
+    for (int r = 0; r < number_of_steps % repeat_move; ++r) {
+        float d = sim.step(0u);
+        ++steps;
+        record();
+        score = fminf(score, d);
+        bool won = (e.flags & FLAG_WON) != 0;
+        if (won && win < 0) win = steps;
+        if (won && early_exit) break;
+    }
+    *win_out = win;
+    *steps_out = steps;
+    *overflow = (e.flags & FLAG_OVERFLOW) ? 1 : 0;
+    return score;
+}
+
+extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, int genome_len, int repeat_move,
+                          int number_of_steps, int early_exit, float* traj, float* score, int* win, int* steps,
+                          int* overflow) {
+    prl_world w;
+    int rc = parse_world_json(json, len, &w);
+    if (rc == PRL_OK) rc = build_dev_world(&w);
+    if (rc != PRL_OK) return rc;
+    const DevWorld& W = w.dev;
+    if (W.n_bodies == 1) *score = rollout<1>(W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow);
+    else if (W.n_bodies == 2) *score = rollout<2>(W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow);
+    else *score = rollout<MAXB>(W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow);
+    return 0;
+}

@@ -1,0 +1,181 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same worlds and move
+sequences. Tolerance: ZERO -- every f32 of every body and every score is compared by bit pattern
+(the kernels are built with -fmad=false and evaluate the reference's expressions in order), which
+is stricter than the north star's "within an f32 tolerance; bit-exact won()/step-of-win"."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import physics_reinforcement_learning_environment_b200 as prl
+from physics_reinforcement_learning_environment_b200 import _lib
+from conftest import WORLDS, random_genomes, synth_world, world_dict, world_text
+from oracle import binding as oracle
+from oracle.binding import OracleEnv
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_rollout_matches_oracle(name):
+    n, L, repeat, steps = 512, 50, 20, 1000
+    genomes = random_genomes(n, L, 21)
+    genomes[:8] = np.arange(8, dtype=np.uint8)[:, None]
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text(name)), n)
+    for early in (True, False):
+        score, win = env.rollout(genomes, repeat, steps, early_exit=early)
+        _, _, run = env.rollout_info()
+        rs, rw, rsteps = oracle.rollout_batch(world_dict(name), genomes, repeat, steps, early, n_threads=os.cpu_count())
+        assert np.array_equal(bits(score), bits(rs))
+        assert np.array_equal(win, rw)
+        assert int(run.sum()) == rsteps
+    env.sync()
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_step_by_step_state_matches_oracle(name):
+    """One kernel launch per step (state round-trips through HBM, manifolds included)."""
+    n, steps, repeat = 8, 600, 10
+    genomes = random_genomes(n, steps // repeat, 33)
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text(name)), n)
+    oracles = [OracleEnv(world_dict(name)) for _ in range(n)]
+    for t in range(steps):
+        mv = np.ascontiguousarray(genomes[:, t // repeat])
+        env.step(mv)
+        for i, o in enumerate(oracles):
+            o.step(int(mv[i]))
+        if t % 7 == 0 or t == steps - 1:
+            st = env.state()
+            ref = np.stack([o.state() for o in oracles])
+            assert np.array_equal(bits(st), bits(ref)), f"step {t + 1}"
+            d = env.distance_to_goals()
+            assert np.array_equal(bits(d), bits(np.array([o.distance_to_goals() for o in oracles], np.float32)))
+            assert np.array_equal(env.won(), np.array([o.won() for o in oracles], np.uint8))
+
+
+def test_uniform_moves_readme_example():
+    """README.md:96-114 / BASELINE config C1: the 8 constant Moves x 1000 steps on right.json."""
+    world = prl.World.from_json(world_text("right"))
+    for mv in range(8):
+        env = prl.BatchedEnvironment(world, 4)
+        env.step_uniform(prl.Move.from_bits(mv), 1000)
+        score, win, run = env.rollout_info()
+        o = OracleEnv(world_dict("right"))
+        best, owin = np.float32(np.inf), -1
+        for t in range(1000):
+            o.step(mv)
+            best = min(best, o.distance_to_goals())
+            if o.won() and owin < 0:
+                owin = t + 1
+        assert np.all(bits(score) == bits(np.float32(best))) and np.all(win == owin) and np.all(run == 1000)
+        assert np.array_equal(bits(env.state()[0]), bits(o.state()))
+
+
+def test_synthetic_64_obstacles_and_edge_case_world():
+    for world in (synth_world(),):
+        text = json.dumps(world)
+        n, L, repeat, steps = 256, 60, 20, 1200
+        genomes = random_genomes(n, L, 5)
+        genomes[:4] = 2
+        genomes[4:8] = 6
+        env = prl.BatchedEnvironment(prl.World.from_json(text), n)
+        score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+        rs, rw, _ = oracle.rollout_batch(world, genomes, repeat, steps, False, n_threads=os.cpu_count())
+        assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
+        env.sync()
+
+
+def test_two_pushable_blocks_rotations_negative_scales():
+    world = {"player_position": [0.0, 40.0], "objects": [
+        {"object": {"Block": {"fixed": True}}, "position": [0.0, -40.0, 1.0], "scale": [-900.0, 50.0], "rotation": 0.05},
+        {"object": {"Block": {"fixed": False}}, "position": [120.0, 10.0, 2.0], "scale": [60.0, -40.0], "rotation": 0.3},
+        {"object": {"Block": {"fixed": False}}, "position": [125.0, 70.0, 3.0], "scale": [50.0, 30.0], "rotation": -0.2},
+        {"object": {"Block": {"fixed": True}}, "position": [-200.0, 0.0, 4.0], "scale": [40.0, 80.0], "rotation": -0.4},
+        {"object": "Goal", "position": [400.0, 0.0, 5.0], "scale": [50.0, 50.0], "rotation": 0.7},
+        {"object": "Goal", "position": [-400.0, 0.0, 6.0], "scale": [-50.0, 50.0], "rotation": 0.0}]}
+    n, L, repeat, steps = 128, 40, 15, 600
+    genomes = random_genomes(n, L, 9)
+    env = prl.BatchedEnvironment(prl.World.from_json(json.dumps(world)), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    rs, rw, _ = oracle.rollout_batch(world, genomes, repeat, steps, False, n_threads=os.cpu_count())
+    assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
+    # final body states too
+    st = env.state(0, 4)
+    for i in range(4):
+        o = OracleEnv(world)
+        for t in range(steps):
+            o.step(int(genomes[i][t // repeat]))
+        assert np.array_equal(bits(st[i]), bits(o.state()))
+
+
+def test_result_is_independent_of_batch_size_and_neighbours():
+    """env i's trajectory must not depend on the batch it sits in (sharding invariance)."""
+    genomes = random_genomes(1000, 50, 77)
+    world = prl.World.from_json(world_text("push"))
+    full = prl.BatchedEnvironment(world, 1000)
+    s_full, w_full = full.rollout(genomes, 20, 1000, early_exit=True)
+    lo, hi = 137, 137 + 301  # an odd-sized slice that straddles warps and blocks
+    part = prl.BatchedEnvironment(world, hi - lo)
+    s_part, w_part = part.rollout(np.ascontiguousarray(genomes[lo:hi]), 20, 1000, early_exit=True)
+    assert np.array_equal(bits(s_full[lo:hi]), bits(s_part)) and np.array_equal(w_full[lo:hi], w_part)
+
+
+def test_full_size_properties_push_65536x2000():
+    """BASELINE config C3 at full size: properties that need no oracle run of the whole batch --
+    duplicated genomes give identical results wherever they sit, every score is a finite
+    non-negative pixel distance, winners have score 0 -- plus an oracle check of a 64-env sample."""
+    n, L, repeat, steps = 65536, 100, 20, 2000
+    genomes = random_genomes(n, L, 0xB200)
+    genomes[n // 2:] = genomes[:n // 2]
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text("push")), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    env.sync()
+    assert np.array_equal(bits(score[:n // 2]), bits(score[n // 2:])) and np.array_equal(win[:n // 2], win[n // 2:])
+    assert np.isfinite(score).all() and (score >= 0).all()
+    assert np.all(score[win > 0] == 0.0) and np.all(win[score > 0] == -1)
+    idx = np.arange(0, n // 2, n // 128)[:64]
+    rs, rw, _ = oracle.rollout_batch(world_dict("push"), np.ascontiguousarray(genomes[idx]), repeat, steps, False,
+                                     n_threads=os.cpu_count())
+    assert np.array_equal(bits(score[idx]), bits(rs)) and np.array_equal(win[idx], rw)
+
+
+def test_reset_and_device_buffers():
+    import torch
+    world = prl.World.from_json(world_text("jump"))
+    n = 300
+    env = prl.BatchedEnvironment(world, n, stream=torch.cuda.current_stream().cuda_stream)
+    genomes = random_genomes(n, 30, 4)
+    s1, w1 = env.rollout(genomes, 20, 600)
+    dg = torch.from_numpy(genomes).cuda()
+    ds = torch.empty(n, dtype=torch.float32, device="cuda")
+    dw = torch.empty(n, dtype=torch.int32, device="cuda")
+    env.rollout(dg, 20, 600, out_score=ds, out_step_of_win=dw)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(ds.cpu().numpy()), bits(s1)) and np.array_equal(dw.cpu().numpy(), w1)
+    # stepping after reset starts again from from_world
+    env.reset()
+    a = env.state()
+    env.step_uniform(2, 50)
+    env.reset()
+    assert np.array_equal(bits(env.state()), bits(a))
+    d = torch.empty(n, dtype=torch.float32, device="cuda")
+    env.distance_to_goals(d)
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(d.cpu().numpy()), bits(env.distance_to_goals()))
+
+
+def test_goalless_world_reports_no_goal():
+    w = prl.World.from_json('{"player_position":[0.0,0.0],"objects":[]}')
+    env = prl.BatchedEnvironment(w, 4)
+    env.step_uniform(0, 3)
+    assert not env.won().any()
+    with pytest.raises(prl.PrlError) as e:
+        env.distance_to_goals()
+    assert e.value.status == _lib.PRL_ERR_NO_GOAL
+    with pytest.raises(prl.PrlError):
+        env.rollout(np.zeros((4, 2), np.uint8), 1, 2)
