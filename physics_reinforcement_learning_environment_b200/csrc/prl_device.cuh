@@ -335,12 +335,22 @@ PRL_D void contact_capsule_cuboid(Manifold& m, const Iso& pos12, float radius, f
     m.n2 = n2;
 }
 
+// sin and cos of a pushable block's rotation increment; kept out of line so the pose update of
+// every body shares one copy of the argument reduction
+#if defined(__CUDA_ARCH__)
+static __device__ __noinline__ void libm_sincosf(float x, float& s, float& c) { s = libm_sinf(x); c = libm_cosf(x); }
+#else
+inline void libm_sincosf(float x, float& s, float& c) { s = libm_sinf(x); c = libm_cosf(x); }
+#endif
+
 // rapier RigidBodyVelocity::integrate with local_com = origin:
-// shift * Isometry::new(linvel*dt, angvel*dt) * shift^-1 * init, then renormalize_fast
-PRL_D Iso integrate_pose(v2 linvel, float angvel, const Iso& init, float dt) {
+// shift * Isometry::new(linvel*dt, angvel*dt) * shift^-1 * init, then renormalize_fast.
+// `locked`: rotations are locked (the player), so angvel is identically zero and the rotation
+// increment is exactly (cos, sin) = (1, 0).
+PRL_D Iso integrate_pose(v2 linvel, float angvel, const Iso& init, float dt, bool locked) {
     v2 com = init.t;
-    float ang = angvel * dt;
-    float rc = libm_cosf(ang), rs = libm_sinf(ang);
+    float rc = 1.0f, rs = 0.0f;
+    if (!locked) libm_sincosf(angvel * dt, rs, rc);
     v2 tr = linvel * dt;
     v2 t = com + tr;
     t = t + rot(rc, rs, -com);
@@ -358,7 +368,20 @@ PRL_D Iso integrate_pose(v2 linvel, float angvel, const Iso& init, float dt) {
 
 // ------------------------------------------------------------------------------------------
 // Per-thread environment. NB = bodies (player + pushable blocks) as a compile-time bound so the
-// body arrays stay in registers; S = manifold slots.
+// body arrays stay in registers; S = manifold slots. Everything indexed at run time lives in
+// thread-local memory as 16-byte rows, so one record moves with one LDL.128 / STL.128.
+struct alignas(16) f4 { float x, y, z, w; };
+
+PRL_D float bits_f32(uint32_t u) {
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+
 template <int NB, int S = MAXC>
 struct Env {
     // rigid bodies (0 = player)
@@ -369,27 +392,35 @@ struct Env {
     uint64_t order;      // nibble k = slot of the k-th live manifold in ascending pair order
     int count;
     uint32_t used;       // bit s = slot s is live
-    int spair[S];        // pair index of slot s
-    int snpts[S];
-    float mf[S][14];     // n1, n2, (p1, p2, dist) x 2
-    // per-step scratch, indexed by slot: solver contacts and velocity constraints
-    float cnx[S], cny[S];            // world normal of the manifold
-    int cn[S];                       // number of solver contacts (0..2)
-    float cpx[S][2], cpy[S][2], cpd[S][2];
-    int cb[S];                       // body1 | body2 << 8 (body1 = 255: ground constraint)
-    float cdx[S], cdy[S], cim1[S], cim2[S], ccfm[S];
-    float ce[S][2][11];              // per point: gcross1, gcross2, rhs, rhs_wo_bias, impulse, r,
-                                     //            t_gcross1, t_gcross2, t_rhs, t_impulse, t_r
+    // mf[s]: the cached contact manifold of one collider pair
+    //   [0] = (hdr, n1.x, n1.y, n2.x)      hdr bits = pair | npts << 8 | n_solver_contacts << 12
+    //   [1] = (n2.y, p1a.x, p1a.y, p2a.x)
+    //   [2] = (p2a.y, dist_a, p1b.x, p1b.y)
+    //   [3] = (p2b.x, p2b.y, dist_b, -)
+    f4 mf[S][4];
+    // sc[s]: its solver contacts (world space), refreshed whenever the narrow phase visits the pair
+    //   [0] = (normal.x, normal.y, pt0.x, pt0.y)   [1] = (dist0, pt1.x, pt1.y, dist1)
+    f4 sc[S][2];
+    // velocity-constraint rows, one per solver contact, in Gauss-Seidel order (per-step scratch)
+    //   [0] = (dir.x, dir.y, inv_mass1, inv_mass2)
+    //   [1] = (gcross1, gcross2, cfm_factor, bodies)   bodies bits = body1 | body2 << 8
+    //   [2] = (rhs, r, impulse, tangent impulse)
+    //   [3] = (t_gcross1, t_gcross2, t_rhs, t_r)
+    f4 row[2 * S][4];
+    float rhs_wo_bias[2 * S];
 };
 
 template <int NB, int S>
 struct Stepper {
     using E = Env<NB, S>;
+    static constexpr int kGround = NB;  // pseudo body index of the fixed world: zero velocity, zero inverse mass
     const DevWorld& W;
     E& e;
     PRL_D Stepper(const DevWorld& w, E& env) : W(w), e(env) {}
 
     PRL_D int slot_at(int k) const { return (int)((e.order >> (4 * k)) & 15u); }
+    PRL_D uint32_t hdr(int slot) const { return f32_bits(e.mf[slot][0].x); }
+    PRL_D int pair_at(int k) const { return (int)(hdr(slot_at(k)) & 0xffu); }
     PRL_D Iso body_pose(int b) const { Iso p; p.t = V(sel(e.x, b), sel(e.y, b)); p.c = sel(e.c, b); p.s = sel(e.s, b); return p; }
     PRL_D Iso collider_pose(int c) const {
         int b = W.body_of[c];
@@ -400,24 +431,53 @@ struct Stepper {
     PRL_D void wake_strong(int b) { e.sleeping &= ~(1u << b); put(e.timer, b, 0.0f); }
 
     PRL_D void load_manifold(int slot, Manifold& m) const {
-        m.npts = e.snpts[slot];
-        const float* f = e.mf[slot];
-        m.n1 = V(f[0], f[1]); m.n2 = V(f[2], f[3]);
-        m.p1[0] = V(f[4], f[5]); m.p2[0] = V(f[6], f[7]); m.dist[0] = f[8];
-        m.p1[1] = V(f[9], f[10]); m.p2[1] = V(f[11], f[12]); m.dist[1] = f[13];
+        f4 a = e.mf[slot][0], b = e.mf[slot][1], c = e.mf[slot][2], d = e.mf[slot][3];
+        m.npts = (int)((f32_bits(a.x) >> 8) & 0xfu);
+        m.n1 = V(a.y, a.z); m.n2 = V(a.w, b.x);
+        m.p1[0] = V(b.y, b.z); m.p2[0] = V(b.w, c.x); m.dist[0] = c.y;
+        m.p1[1] = V(c.z, c.w); m.p2[1] = V(d.x, d.y); m.dist[1] = d.z;
     }
-    PRL_D void store_manifold(int slot, const Manifold& m) {
-        e.snpts[slot] = m.npts;
-        float* f = e.mf[slot];
-        f[0] = m.n1.x; f[1] = m.n1.y; f[2] = m.n2.x; f[3] = m.n2.y;
-        f[4] = m.p1[0].x; f[5] = m.p1[0].y; f[6] = m.p2[0].x; f[7] = m.p2[0].y; f[8] = m.dist[0];
-        f[9] = m.p1[1].x; f[10] = m.p1[1].y; f[11] = m.p2[1].x; f[12] = m.p2[1].y; f[13] = m.dist[1];
+    // store a manifold with points and refresh its solver contacts (rapier
+    // NarrowPhase::compute_contacts tail: points with dist < prediction, at the midpoint between
+    // the two surfaces, in world space)
+    PRL_D void store_manifold(int slot, int pair, const Manifold& m, const Iso& pose1) {
+        v2 normal = rot(pose1.c, pose1.s, m.n1);
+        int ns = 0;
+        float px[2] = {0.0f, 0.0f}, py[2] = {0.0f, 0.0f}, pd[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k < m.npts && m.dist[k] < W.prediction) {
+                v2 wp = xform(pose1, m.p1[k]);
+                v2 half = normal * m.dist[k];
+                float qx = wp.x + half.x / 2.0f, qy = wp.y + half.y / 2.0f;
+                if (ns == 0) { px[0] = qx; py[0] = qy; pd[0] = m.dist[k]; }
+                else { px[1] = qx; py[1] = qy; pd[1] = m.dist[k]; }
+                ++ns;
+            }
+        }
+        f4 a, b, c, d;
+        a.x = bits_f32((uint32_t)pair | ((uint32_t)m.npts << 8) | ((uint32_t)ns << 12));
+        a.y = m.n1.x; a.z = m.n1.y; a.w = m.n2.x;
+        b.x = m.n2.y; b.y = m.p1[0].x; b.z = m.p1[0].y; b.w = m.p2[0].x;
+        c.x = m.p2[0].y; c.y = m.dist[0]; c.z = m.p1[1].x; c.w = m.p1[1].y;
+        d.x = m.p2[1].x; d.y = m.p2[1].y; d.z = m.dist[1]; d.w = 0.0f;
+        e.mf[slot][0] = a; e.mf[slot][1] = b; e.mf[slot][2] = c; e.mf[slot][3] = d;
+        f4 s0, s1;
+        s0.x = normal.x; s0.y = normal.y; s0.z = px[0]; s0.w = py[0];
+        s1.x = pd[0]; s1.y = px[1]; s1.z = py[1]; s1.w = pd[1];
+        e.sc[slot][0] = s0; e.sc[slot][1] = s1;
     }
-    // position in the sorted list of pair p, or -1
-    PRL_D int find(int p) const {
-        int r = -1;
-        for (int k = 0; k < e.count; ++k) if (e.spair[slot_at(k)] == p) r = k;
-        return r;
+    // after a load from HBM: solver contacts are a pure function of the manifold and collider 1's
+    // pose, so they are not part of the stored state
+    PRL_D void refresh_solver_contacts() {
+#pragma unroll 1
+        for (int k = 0; k < e.count; ++k) {
+            int slot = slot_at(k);
+            Manifold m;
+            load_manifold(slot, m);
+            int p = (int)(hdr(slot) & 0xffu);
+            store_manifold(slot, p, m, collider_pose(W.pair_c1[p]));
+        }
     }
     PRL_D void remove_at(int k) {
         int slot = slot_at(k);
@@ -427,46 +487,16 @@ struct Stepper {
         e.order = low | high;
         --e.count;
     }
-    // allocate a slot for pair p and link it at its sorted position; -1 on overflow
-    PRL_D int insert(int p) {
+    // allocate a slot and link it at sorted position k; -1 on overflow
+    PRL_D int insert_at(int k) {
         int slot = first_zero_bit(e.used);
         if (slot >= S) { e.flags |= FLAG_OVERFLOW; return -1; }
-        int k = 0;
-        while (k < e.count && e.spair[slot_at(k)] < p) ++k;
         uint64_t low = k == 0 ? 0ull : (e.order & (~0ull >> (64 - 4 * k)));
         uint64_t high = k == 0 ? e.order : (e.order >> (4 * k));
         e.order = low | ((uint64_t)slot << (4 * k)) | (k >= 15 ? 0ull : (high << (4 * (k + 1))));
         e.used |= 1u << slot;
-        e.spair[slot] = p;
         ++e.count;
         return slot;
-    }
-
-    // rapier NarrowPhase::compute_contacts tail: solver contacts of one manifold. They are a pure
-    // function of the cached manifold and collider 1's pose, which cannot change between the end
-    // of one pipeline step and the constraint build of the next, so they are recomputed here
-    // rather than stored.
-    PRL_D void solver_contacts(int slot) {
-        int p = e.spair[slot];
-        Iso pose1 = collider_pose(W.pair_c1[p]);
-        Manifold m;
-        load_manifold(slot, m);
-        v2 normal = rot(pose1.c, pose1.s, m.n1);
-        int ns = 0;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (k < m.npts && m.dist[k] < W.prediction) {
-                v2 wp = xform(pose1, m.p1[k]);
-                v2 half = normal * m.dist[k];
-                e.cpx[slot][ns] = wp.x + half.x / 2.0f;
-                e.cpy[slot][ns] = wp.y + half.y / 2.0f;
-                e.cpd[slot][ns] = m.dist[k];
-                ++ns;
-            }
-        }
-        e.cnx[slot] = normal.x;
-        e.cny[slot] = normal.y;
-        e.cn[slot] = ns;
     }
 
     // rapier RigidBody::apply_impulse; a zero impulse neither moves nor wakes the body
@@ -489,55 +519,65 @@ struct Stepper {
         }
     }
 
-    // common.rs:216-313: ground-contact scan over the player's contact pairs, then the move impulses
+    // common.rs:216-313: ground-contact scan over the player's contact pairs, then the move
+    // impulses. The player's pairs are the head of the sorted manifold list.
     PRL_D void player_move(uint32_t mv) {
         v2 lower = V(e.x[0], e.y[0] - W.lower_off);
         int nfc = 0;
         v2 pmin = V(0.0f, 0.0f), pmax = V(0.0f, 0.0f);
         int bmin = -1, bmax = -1;
-        int nplayer = 0;  // live manifolds of player pairs: the head of the sorted list
+        int nplayer = 0;
+#pragma unroll 1
         for (int k = 0; k < e.count; ++k) {
             int slot = slot_at(k);
-            int p = e.spair[slot];
+            uint32_t h = hdr(slot);
+            int p = (int)(h & 0xffu), ns = (int)(h >> 12);
             if (p >= W.n_player_pairs) break;
             ++nplayer;
             int body = W.body_of[W.pair_c2[p]];
-            for (int i = 0; i < e.cn[slot]; ++i) {
-                v2 pt = V(e.cpx[slot][i], e.cpy[slot][i]);
-                v2 q = pt - lower;
-                q = V(q.x / W.radius, q.y / W.radius);
-                if (q.y < -0.707f) {
-                    if (nfc == 0 || pt.x < pmin.x) { pmin = pt; bmin = body; }    // min_by: first minimum
-                    if (nfc == 0 || !(pt.x < pmax.x)) { pmax = pt; bmax = body; } // max_by: last maximum
-                    ++nfc;
+            f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                if (i < ns) {
+                    v2 pt = i == 0 ? V(s0.z, s0.w) : V(s1.y, s1.z);
+                    v2 q = pt - lower;
+                    q = V(q.x / W.radius, q.y / W.radius);
+                    if (q.y < -0.707f) {
+                        if (nfc == 0 || pt.x < pmin.x) { pmin = pt; bmin = body; }    // min_by: first minimum
+                        if (nfc == 0 || !(pt.x < pmax.x)) { pmax = pt; bmax = body; } // max_by: last maximum
+                        ++nfc;
+                    }
                 }
             }
         }
         if (nfc == 0) return;
         v2 player_impulse = V(0.0f, 0.0f);
-        if (mv & 1u) {
-            v2 n = pmin - lower;
-            float len = sqrtf(n.x * n.x + n.y * n.y);
-            n = V(n.x / len, n.y / len);
-            v2 imp = V(0.003f * n.y, -0.003f * n.x);
-            if (NB > 1 && bmin >= 0) apply_impulse_at_point(bmin, -imp, pmin);
-            player_impulse = player_impulse + imp;
+        // left / right: tangent impulse at the extreme floor contact (common.rs:249-295)
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            if (mv & (1u << side)) {
+                v2 pt = side == 0 ? pmin : pmax;
+                int body = side == 0 ? bmin : bmax;
+                v2 n = pt - lower;
+                float len = sqrtf(n.x * n.x + n.y * n.y);
+                n = V(n.x / len, n.y / len);
+                v2 imp = side == 0 ? V(0.003f * n.y, -0.003f * n.x) : V(-0.003f * n.y, 0.003f * n.x);
+                if (NB > 1 && body >= 0) apply_impulse_at_point(body, -imp, pt);
+                player_impulse = player_impulse + imp;
+            }
         }
-        if (mv & 2u) {
-            v2 n = pmax - lower;
-            float len = sqrtf(n.x * n.x + n.y * n.y);
-            n = V(n.x / len, n.y / len);
-            v2 imp = V(-0.003f * n.y, 0.003f * n.x);
-            if (NB > 1 && bmax >= 0) apply_impulse_at_point(bmax, -imp, pmax);
-            player_impulse = player_impulse + imp;
-        }
-        if (mv & 4u) {
+        if (mv & 4u) {  // up: the jump impulse is shared by all floor contacts (common.rs:297-310)
             float cnt = (float)nfc;
+#pragma unroll 1
             for (int k = 0; k < nplayer; ++k) {
                 int slot = slot_at(k);
-                int body = W.body_of[W.pair_c2[e.spair[slot]]];
-                for (int i = 0; i < e.cn[slot]; ++i) {
-                    v2 pt = V(e.cpx[slot][i], e.cpy[slot][i]);
+                uint32_t h = hdr(slot);
+                int ns = (int)(h >> 12);
+                int body = W.body_of[W.pair_c2[h & 0xffu]];
+                f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
+#pragma unroll 1
+                for (int i = 0; i < ns; ++i) {
+                    v2 pt = i == 0 ? V(s0.z, s0.w) : V(s1.y, s1.z);
                     v2 q = pt - lower;
                     q = V(q.x / W.radius, q.y / W.radius);
                     if (q.y < -0.707f) {
@@ -572,15 +612,20 @@ struct Stepper {
             }
         }
         if (NB > 1) {
-            for (int round = 0; round < NB - 1; ++round) {
-                for (int k = 0; k < e.count; ++k) {
-                    int slot = slot_at(k);
-                    if (e.cn[slot] == 0) continue;
-                    int p = e.spair[slot];
-                    int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
-                    if (b1 < 0 || b2 < 0) continue;
-                    uint32_t m1 = 1u << b1, m2 = 1u << b2;
-                    if ((reached & m1) || (reached & m2)) reached |= m1 | m2;
+            // a graph walk is only needed if some body is asleep or about to be
+            if ((e.sleeping | tentative) != 0) {
+#pragma unroll 1
+                for (int round = 0; round < NB - 1; ++round) {
+#pragma unroll 1
+                    for (int k = 0; k < e.count; ++k) {
+                        uint32_t h = hdr(slot_at(k));
+                        if ((h >> 12) == 0) continue;
+                        int p = (int)(h & 0xffu);
+                        int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
+                        if (b1 < 0 || b2 < 0) continue;
+                        uint32_t m1 = 1u << b1, m2 = 1u << b2;
+                        if ((reached & m1) || (reached & m2)) reached |= m1 | m2;
+                    }
                 }
             }
         }
@@ -595,12 +640,17 @@ struct Stepper {
         }
     }
 
-    // rapier VelocityConstraint::generate / VelocityGroundConstraint::generate for one manifold
-    PRL_D void generate_constraint(int slot) {
-        int p = e.spair[slot];
+    // rapier VelocityConstraint::generate / VelocityGroundConstraint::generate for one manifold:
+    // appends one row per solver contact. A one-body ("ground") constraint is written as a
+    // two-body row against the pseudo body kGround (zero velocity, zero inverse mass, zero
+    // angular response), which evaluates to the same values as rapier's ground formulas.
+    PRL_D int generate_constraint(int slot, int nrows) {
+        uint32_t h = hdr(slot);
+        int p = (int)(h & 0xffu), ns = (int)(h >> 12);
         int h1 = W.body_of[W.pair_c1[p]], h2 = W.body_of[W.pair_c2[p]];
         bool two_body = h1 >= 0 && h2 >= 0;
-        v2 normal = V(e.cnx[slot], e.cny[slot]);
+        f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
+        v2 normal = V(s0.x, s0.y);
         v2 dir1;
         if (two_body) dir1 = -normal;
         else if (h2 < 0) { h2 = h1; h1 = -1; dir1 = normal; }  // the dynamic body becomes body 2
@@ -610,7 +660,7 @@ struct Stepper {
         v2 v2_ = V(sel(e.vx, h2), sel(e.vy, h2)), com2 = V(sel(e.x, h2), sel(e.y, h2));
         float w2 = sel(e.w, h2), im2 = W.inv_mass[h2], ii2 = W.inv_inertia_sqrt[h2];
         float ccd = W.ccd_thickness[h2];
-        if (two_body) {
+        if (NB > 1 && two_body) {
             v1 = V(sel(e.vx, h1), sel(e.vy, h1));
             com1 = V(sel(e.x, h1), sel(e.y, h1));
             w1 = sel(e.w, h1);
@@ -619,125 +669,99 @@ struct Stepper {
             ccd = W.ccd_thickness[h1] + W.ccd_thickness[h2];
         }
         v2 tan1 = V(-dir1.y, dir1.x);
-        e.cb[slot] = (two_body ? h1 : 255) | (h2 << 8);
-        e.cdx[slot] = dir1.x;
-        e.cdy[slot] = dir1.y;
-        e.cim1[slot] = im1;
-        e.cim2[slot] = im2;
+        float bodies = bits_f32((uint32_t)(two_body ? h1 : kGround) | ((uint32_t)h2 << 8));
         bool fast = false;
-        for (int k = 0; k < e.cn[slot]; ++k) {
-            v2 pt = V(e.cpx[slot][k], e.cpy[slot][k]);
-            float dist = e.cpd[slot][k];
+#pragma unroll 1
+        for (int k = 0; k < ns; ++k) {
+            v2 pt = k == 0 ? V(s0.z, s0.w) : V(s1.y, s1.z);
+            float dist = k == 0 ? s1.x : s1.w;
             v2 dp1 = pt - com1, dp2 = pt - com2;
             v2 vel1 = v1 + wcross(w1, dp1);
             v2 vel2 = v2_ + wcross(w2, dp2);
-            float* el = e.ce[slot][k];
-            {
-                float gcross2 = ii2 * cross(dp2, -dir1);
-                float gcross1 = 0.0f, pm;
-                if (two_body) {
-                    gcross1 = ii1 * cross(dp1, dir1);
-                    float imsum = im1 + im2;
-                    pm = inv0(dot(dir1, dir1 * imsum) + gcross1 * gcross1 + gcross2 * gcross2);
-                } else {
-                    pm = inv0(dot(dir1, dir1 * im2) + gcross2 * gcross2);
-                }
-                float rhs_wo_bias = (1.0f + 0.0f * 0.0f) * dot(vel1 - vel2, dir1);
-                rhs_wo_bias += fmaxf(dist, 0.0f) * W.inv_dt;
-                rhs_wo_bias *= 0.0f + 1.0f;
-                float pen = dist + W.allowed_linear_error;
-                pen = fminf(fmaxf(pen, -kFltMax), 0.0f);
-                float rhs_bias = W.erp_inv_dt * pen;
-                float rhs = rhs_wo_bias + rhs_bias;
-                fast = fast || (-rhs * W.dt > ccd * 0.5f);
-                el[0] = gcross1; el[1] = gcross2; el[2] = rhs; el[3] = rhs_wo_bias; el[4] = 0.0f; el[5] = pm;
+            f4 r0, r1, r2, r3;
+            float gcross2 = ii2 * cross(dp2, -dir1);
+            float gcross1 = 0.0f, pm;
+            if (NB > 1 && two_body) {
+                gcross1 = ii1 * cross(dp1, dir1);
+                float imsum = im1 + im2;
+                pm = inv0(dot(dir1, dir1 * imsum) + gcross1 * gcross1 + gcross2 * gcross2);
+            } else {
+                pm = inv0(dot(dir1, dir1 * im2) + gcross2 * gcross2);
             }
-            {
-                float gcross2 = ii2 * cross(dp2, -tan1);
-                float gcross1 = 0.0f, r;
-                if (two_body) {
-                    gcross1 = ii1 * cross(dp1, tan1);
-                    float imsum = im1 + im2;
-                    r = dot(tan1, tan1 * imsum) + gcross1 * gcross1 + gcross2 * gcross2;
-                } else {
-                    r = dot(tan1, tan1 * im2) + gcross2 * gcross2;
-                }
-                v2 dv = (vel1 - vel2) + V(0.0f, 0.0f);
-                el[6] = gcross1; el[7] = gcross2; el[8] = dot(dv, tan1); el[9] = 0.0f; el[10] = inv0(r);
+            float rhs_wo_bias = (1.0f + 0.0f * 0.0f) * dot(vel1 - vel2, dir1);
+            rhs_wo_bias += fmaxf(dist, 0.0f) * W.inv_dt;
+            rhs_wo_bias *= 0.0f + 1.0f;
+            float pen = dist + W.allowed_linear_error;
+            pen = fminf(fmaxf(pen, -kFltMax), 0.0f);
+            float rhs_bias = W.erp_inv_dt * pen;
+            float rhs = rhs_wo_bias + rhs_bias;
+            fast = fast || (-rhs * W.dt > ccd * 0.5f);
+            float t_gcross2 = ii2 * cross(dp2, -tan1);
+            float t_gcross1 = 0.0f, tr;
+            if (NB > 1 && two_body) {
+                t_gcross1 = ii1 * cross(dp1, tan1);
+                float imsum = im1 + im2;
+                tr = dot(tan1, tan1 * imsum) + t_gcross1 * t_gcross1 + t_gcross2 * t_gcross2;
+            } else {
+                tr = dot(tan1, tan1 * im2) + t_gcross2 * t_gcross2;
             }
+            v2 dv = (vel1 - vel2) + V(0.0f, 0.0f);
+            r0.x = dir1.x; r0.y = dir1.y; r0.z = im1; r0.w = im2;
+            r1.x = gcross1; r1.y = gcross2; r1.z = W.cfm_factor; r1.w = bodies;
+            r2.x = rhs; r2.y = pm; r2.z = 0.0f; r2.w = 0.0f;
+            r3.x = t_gcross1; r3.y = t_gcross2; r3.z = dot(dv, tan1); r3.w = inv0(tr);
+            int j = nrows + k;
+            e.row[j][0] = r0; e.row[j][1] = r1; e.row[j][2] = r2; e.row[j][3] = r3;
+            e.rhs_wo_bias[j] = rhs_wo_bias;
         }
-        e.ccfm[slot] = fast ? 1.0f : W.cfm_factor;
+        if (fast) {  // a fast contact makes the whole constraint rigid (cfm_factor 1)
+#pragma unroll 1
+            for (int k = 0; k < ns; ++k) e.row[nrows + k][1].z = 1.0f;
+        }
+        return nrows + ns;
     }
 
-    // rapier VelocityConstraintElement::solve_group / VelocityGroundConstraintElement::solve_group
-    PRL_D void solve_constraint(int slot, bool normal_part, bool friction_part, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
-        int b1 = e.cb[slot] & 255, b2 = e.cb[slot] >> 8;
-        v2 dir1 = V(e.cdx[slot], e.cdy[slot]);
-        v2 tan1 = V(-dir1.y, dir1.x);
-        float im2 = e.cim2[slot];
-        v2 l2 = V(sel(dlx, b2), sel(dly, b2));
-        float a2 = sel(da, b2);
-        int n = e.cn[slot];
-        if (NB > 1 && b1 != 255) {
-            float im1 = e.cim1[slot];
-            v2 l1 = V(sel(dlx, b1), sel(dly, b1));
-            float a1 = sel(da, b1);
-            if (normal_part) {
-                float cfm = e.ccfm[slot];
-                for (int k = 0; k < n; ++k) {
-                    float* el = e.ce[slot][k];
-                    float dvel = dot(dir1, l1) + el[0] * a1 - dot(dir1, l2) + el[1] * a2 + el[2];
-                    float ni = cfm * fmaxf(el[4] - el[5] * dvel, 0.0f);
-                    float dl = ni - el[4];
-                    el[4] = ni;
-                    l1 = l1 + (dir1 * im1) * dl;
-                    a1 += el[0] * dl;
-                    l2 = l2 + (dir1 * im2) * -dl;
-                    a2 += el[1] * dl;
-                }
-            }
-            if (friction_part) {
-                for (int k = 0; k < n; ++k) {
-                    float* el = e.ce[slot][k];
-                    float limit = kFriction * el[4];
-                    float dvel = dot(tan1, l1) + el[6] * a1 - dot(tan1, l2) + el[7] * a2 + el[8];
-                    float ni = fminf(fmaxf(el[9] - el[10] * dvel, -limit), limit);
-                    float dl = ni - el[9];
-                    el[9] = ni;
-                    l1 = l1 + (tan1 * im1) * dl;
-                    a1 += el[6] * dl;
-                    l2 = l2 + (tan1 * im2) * -dl;
-                    a2 += el[7] * dl;
-                }
-            }
-            put(dlx, b1, l1.x); put(dly, b1, l1.y); put(da, b1, a1);
+    // One Gauss-Seidel row update: rapier VelocityConstraintElement::solve_group, normal part or
+    // friction part. Ground rows use body1 = kGround, whose increments stay zero.
+    PRL_D void solve_row(int j, bool normal_part, float (&dlx)[NB + 1], float (&dly)[NB + 1], float (&da)[NB + 1]) {
+        f4 r0 = e.row[j][0], r2 = e.row[j][2];
+        v2 dir1 = V(r0.x, r0.y);
+        float im1 = r0.z, im2 = r0.w;
+        if (normal_part) {
+            f4 r1 = e.row[j][1];
+            uint32_t bodies = f32_bits(r1.w);
+            int b1 = (int)(bodies & 0xffu), b2 = (int)(bodies >> 8);
+            v2 l1 = V(sel(dlx, b1), sel(dly, b1)), l2 = V(sel(dlx, b2), sel(dly, b2));
+            float a1 = sel(da, b1), a2 = sel(da, b2);
+            float dvel = dot(dir1, l1) + r1.x * a1 - dot(dir1, l2) + r1.y * a2 + r2.x;
+            float ni = r1.z * fmaxf(r2.z - r2.y * dvel, 0.0f);
+            float dl = ni - r2.z;
+            e.row[j][2].z = ni;
+            l1 = l1 + (dir1 * im1) * dl;
+            a1 += r1.x * dl;
+            l2 = l2 + (dir1 * im2) * -dl;
+            a2 += r1.y * dl;
+            if (NB > 1) { put(dlx, b1, l1.x); put(dly, b1, l1.y); put(da, b1, a1); }
+            put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
         } else {
-            if (normal_part) {
-                float cfm = e.ccfm[slot];
-                for (int k = 0; k < n; ++k) {
-                    float* el = e.ce[slot][k];
-                    float dvel = -dot(dir1, l2) + el[1] * a2 + el[2];
-                    float ni = cfm * fmaxf(el[4] - el[5] * dvel, 0.0f);
-                    float dl = ni - el[4];
-                    el[4] = ni;
-                    l2 = l2 + (dir1 * im2) * -dl;
-                    a2 += el[1] * dl;
-                }
-            }
-            if (friction_part) {
-                for (int k = 0; k < n; ++k) {
-                    float* el = e.ce[slot][k];
-                    float limit = kFriction * el[4];
-                    float dvel = -dot(tan1, l2) + el[7] * a2 + el[8];
-                    float ni = fminf(fmaxf(el[9] - el[10] * dvel, -limit), limit);
-                    float dl = ni - el[9];
-                    el[9] = ni;
-                    l2 = l2 + (tan1 * im2) * -dl;
-                    a2 += el[7] * dl;
-                }
-            }
+            f4 r3 = e.row[j][3];
+            uint32_t bodies = f32_bits(e.row[j][1].w);
+            int b1 = (int)(bodies & 0xffu), b2 = (int)(bodies >> 8);
+            v2 tan1 = V(-dir1.y, dir1.x);
+            v2 l1 = V(sel(dlx, b1), sel(dly, b1)), l2 = V(sel(dlx, b2), sel(dly, b2));
+            float a1 = sel(da, b1), a2 = sel(da, b2);
+            float limit = kFriction * r2.z;
+            float dvel = dot(tan1, l1) + r3.x * a1 - dot(tan1, l2) + r3.y * a2 + r3.z;
+            float ni = fminf(fmaxf(r2.w - r3.w * dvel, -limit), limit);
+            float dl = ni - r2.w;
+            e.row[j][2].w = ni;
+            l1 = l1 + (tan1 * im1) * dl;
+            a1 += r3.x * dl;
+            l2 = l2 + (tan1 * im2) * -dl;
+            a2 += r3.y * dl;
+            if (NB > 1) { put(dlx, b1, l1.x); put(dly, b1, l1.y); put(da, b1, a1); }
+            put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
         }
-        put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
     }
 
     // rapier islands + constraint build + VelocitySolver::solve + position update for the
@@ -745,62 +769,59 @@ struct Stepper {
     PRL_D uint32_t solve_and_integrate() {
         update_active_set();
         uint32_t active = ~e.sleeping & ((1u << W.n_bodies) - 1u);
-        // constraints: two-body manifolds first, then one-body ("ground") ones, each in pair order
-        uint64_t cons = 0;
-        int ncons = 0;
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
-            if (NB == 1 && pass == 0) continue;
+        // constraint rows: two-body manifolds first, then one-body ("ground") ones, each in pair order
+        int nrows = 0;
+#pragma unroll 1
+        for (int pass = NB == 1 ? 1 : 0; pass < 2; ++pass) {
+#pragma unroll 1
             for (int k = 0; k < e.count; ++k) {
                 int slot = slot_at(k);
-                if (e.cn[slot] == 0) continue;
-                int p = e.spair[slot];
+                uint32_t h = hdr(slot);
+                if ((h >> 12) == 0) continue;
+                int p = (int)(h & 0xffu);
                 int h1 = W.body_of[W.pair_c1[p]], h2 = W.body_of[W.pair_c2[p]];
                 bool two_body = h1 >= 0 && h2 >= 0;
                 if ((pass == 0) != two_body) continue;
                 bool awake1 = h1 >= 0 && ((active >> h1) & 1u);
                 bool awake2 = h2 >= 0 && ((active >> h2) & 1u);
                 if (!awake1 && !awake2) continue;
-                cons |= (uint64_t)slot << (4 * ncons);
-                ++ncons;
+                nrows = generate_constraint(slot, nrows);
             }
         }
-        for (int i = 0; i < ncons; ++i) generate_constraint((int)((cons >> (4 * i)) & 15u));
-
-        float dlx[NB], dly[NB], da[NB];
+        float dlx[NB + 1], dly[NB + 1], da[NB + 1];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             dlx[b] = b < W.n_bodies ? W.gdv_x[b] : 0.0f;
             dly[b] = b < W.n_bodies ? W.gdv_y[b] : 0.0f;
             da[b] = 0.0f;
         }
-        // 4 velocity iterations with interleaved friction, then the 4 remaining friction iterations
-        for (int it = 0; it < 4; ++it) {
-            for (int i = 0; i < ncons; ++i) solve_constraint((int)((cons >> (4 * i)) & 15u), true, false, dlx, dly, da);
-            for (int i = 0; i < ncons; ++i) solve_constraint((int)((cons >> (4 * i)) & 15u), false, true, dlx, dly, da);
-        }
-        for (int it = 0; it < 4; ++it)
-            for (int i = 0; i < ncons; ++i) solve_constraint((int)((cons >> (4 * i)) & 15u), false, true, dlx, dly, da);
-        // positions integrate the biased velocities
+        dlx[NB] = 0.0f; dly[NB] = 0.0f; da[NB] = 0.0f;
         float nx[NB], ny[NB], nc[NB], ns[NB];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
-            nx[b] = e.x[b]; ny[b] = e.y[b]; nc[b] = e.c[b]; ns[b] = e.s[b];
-            if ((active >> b) & 1u) {
-                float dangvel = W.inv_inertia_sqrt[b] * da[b];
-                Iso init; init.t = V(e.x[b], e.y[b]); init.c = e.c[b]; init.s = e.s[b];
-                Iso np = integrate_pose(V(e.vx[b] + dlx[b], e.vy[b] + dly[b]), e.w[b] + dangvel, init, W.dt);
-                nx[b] = np.t.x; ny[b] = np.t.y; nc[b] = np.c; ns[b] = np.s;
+        for (int b = 0; b < NB; ++b) { nx[b] = e.x[b]; ny[b] = e.y[b]; nc[b] = e.c[b]; ns[b] = e.s[b]; }
+        // sweep schedule (rapier VelocitySolver::solve with 4 velocity, 8 friction and 1
+        // stabilisation iteration): N F N F N F N F F F F F | integrate, drop bias | N F
+#pragma unroll 1
+        for (int sweep = 0; sweep < 14; ++sweep) {
+            if (sweep == 12) {
+                // positions integrate the biased velocities
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if ((active >> b) & 1u) {
+                        float dangvel = W.inv_inertia_sqrt[b] * da[b];
+                        Iso init; init.t = V(e.x[b], e.y[b]); init.c = e.c[b]; init.s = e.s[b];
+                        Iso np = integrate_pose(V(e.vx[b] + dlx[b], e.vy[b] + dly[b]), e.w[b] + dangvel, init, W.dt, b == 0);
+                        nx[b] = np.t.x; ny[b] = np.t.y; nc[b] = np.c; ns[b] = np.s;
+                    }
+                }
+                // the stabilisation sweep runs without the penetration bias and without softness
+#pragma unroll 1
+                for (int j = 0; j < nrows; ++j) { e.row[j][2].x = e.rhs_wo_bias[j]; e.row[j][1].z = 1.0f; }
             }
+            bool normal_part = sweep == 12 || (sweep < 8 && (sweep & 1) == 0);
+#pragma unroll 1
+            for (int j = 0; j < nrows; ++j) solve_row(j, normal_part, dlx, dly, da);
         }
-        // one stabilisation sweep without the penetration bias, then the final velocities
-        for (int i = 0; i < ncons; ++i) {
-            int slot = (int)((cons >> (4 * i)) & 15u);
-            e.ccfm[slot] = 1.0f;
-            for (int k = 0; k < e.cn[slot]; ++k) e.ce[slot][k][2] = e.ce[slot][k][3];
-        }
-        for (int i = 0; i < ncons; ++i) solve_constraint((int)((cons >> (4 * i)) & 15u), true, false, dlx, dly, da);
-        for (int i = 0; i < ncons; ++i) solve_constraint((int)((cons >> (4 * i)) & 15u), false, true, dlx, dly, da);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             if ((active >> b) & 1u) {
@@ -814,12 +835,25 @@ struct Stepper {
         return active;
     }
 
+    // loosened AABB overlap of pair p and whether one of its colliders moved
+    PRL_D bool pair_overlaps(int p, uint32_t moved, bool all, const float (&bmnx)[NB], const float (&bmny)[NB], const float (&bmxx)[NB],
+                             const float (&bmxy)[NB], bool& modified) const {
+        int c1 = W.pair_c1[p], c2 = W.pair_c2[p];
+        int b1 = W.body_of[c1], b2 = W.body_of[c2];
+        modified = all || (b1 >= 0 && ((moved >> b1) & 1u)) || (b2 >= 0 && ((moved >> b2) & 1u));
+        float amnx, amny, amxx, amxy, qmnx, qmny, qmxx, qmxy;
+        if (b1 >= 0) { amnx = sel(bmnx, b1); amny = sel(bmny, b1); amxx = sel(bmxx, b1); amxy = sel(bmxy, b1); }
+        else { amnx = W.amnx[c1]; amny = W.amny[c1]; amxx = W.amxx[c1]; amxy = W.amxy[c1]; }
+        if (b2 >= 0) { qmnx = sel(bmnx, b2); qmny = sel(bmny, b2); qmxx = sel(bmxx, b2); qmxy = sel(bmxy, b2); }
+        else { qmnx = W.amnx[c2]; qmny = W.amny[c2]; qmxx = W.amxx[c2]; qmxy = W.amxy[c2]; }
+        return amnx <= qmxx && qmnx <= amxx && amny <= qmxy && qmny <= amxy;
+    }
+
     // rapier PhysicsPipeline::detect_collisions for the colliders of the bodies in `moved`
     // (`all` on the first step): loosened-AABB broad phase, then the narrow phase on the
     // overlapping pairs. A brute-force AABB test over the world's candidate pairs is
     // result-equivalent to rapier's sweep-and-prune.
     PRL_D void detect_collisions(uint32_t moved, bool all) {
-        // loosened AABBs of the body colliders
         float bmnx[NB], bmny[NB], bmxx[NB], bmxy[NB];
         {
             // player capsule: segment endpoints +- radius
@@ -844,91 +878,88 @@ struct Stepper {
                 bmnx[b] = bmny[b] = bmxx[b] = bmxy[b] = 0.0f;
             }
         }
-        auto pair_overlaps = [&](int p, bool& modified) -> bool {
-            int c1 = W.pair_c1[p], c2 = W.pair_c2[p];
-            int b1 = W.body_of[c1], b2 = W.body_of[c2];
-            modified = all || (b1 >= 0 && ((moved >> b1) & 1u)) || (b2 >= 0 && ((moved >> b2) & 1u));
-            float amnx, amny, amxx, amxy, qmnx, qmny, qmxx, qmxy;
-            if (b1 >= 0) { amnx = sel(bmnx, b1); amny = sel(bmny, b1); amxx = sel(bmxx, b1); amxy = sel(bmxy, b1); }
-            else { amnx = W.amnx[c1]; amny = W.amny[c1]; amxx = W.amxx[c1]; amxy = W.amxy[c1]; }
-            if (b2 >= 0) { qmnx = sel(bmnx, b2); qmny = sel(bmny, b2); qmxx = sel(bmxx, b2); qmxy = sel(bmxy, b2); }
-            else { qmnx = W.amnx[c2]; qmny = W.amny[c2]; qmxx = W.amxx[c2]; qmxy = W.amxy[c2]; }
-            return amnx <= qmxx && qmnx <= amxx && amny <= qmxy && qmny <= amxy;
-        };
-        // 1. manifolds whose pair left the broad phase: NarrowPhase::remove_pair wakes both
-        //    bodies if the pair had an active contact
-        for (int k = e.count - 1; k >= 0; --k) {
-            int slot = slot_at(k);
-            int p = e.spair[slot];
-            bool modified;
-            bool ov = pair_overlaps(p, modified);
-            if (modified && !ov) {
-                bool active_contact = false;
-                const float* f = e.mf[slot];
-                if (e.snpts[slot] > 0 && f[8] < W.prediction) active_contact = true;
-                if (e.snpts[slot] > 1 && f[13] < W.prediction) active_contact = true;
-                if (active_contact) {
-                    int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
-                    if (b1 >= 0) wake_strong(b1);
-                    if (b2 >= 0) wake_strong(b2);
-                }
-                remove_at(k);
-            }
-        }
-        // 2. overlapping pairs with a moved collider, in ascending pair order
+        // Broad phase over the world's candidate pairs (ascending), merged with the sorted manifold
+        // list: a pair that left the broad phase drops its manifold (NarrowPhase::remove_pair wakes
+        // both bodies if it had an active contact); an overlapping pair with a moved collider
+        // becomes a narrow-phase candidate.
         int cand[S];
         int ncand = 0;
-        for (int p = 0; p < W.n_pairs; ++p) {
-            bool modified;
-            bool ov = pair_overlaps(p, modified);
-            if (modified && ov) {
-                if (ncand < S) cand[ncand++] = p;
-                else e.flags |= FLAG_OVERFLOW;
+        {
+            int k = 0;  // position in the sorted manifold list of the first entry with pair >= p
+#pragma unroll 1
+            for (int p = 0; p < W.n_pairs; ++p) {
+                bool modified;
+                bool ov = pair_overlaps(p, moved, all, bmnx, bmny, bmxx, bmxy, modified);
+                bool have = k < e.count && pair_at(k) == p;
+                if (modified && !ov && have) {
+                    if ((hdr(slot_at(k)) >> 12) != 0) {
+                        int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
+                        if (b1 >= 0) wake_strong(b1);
+                        if (b2 >= 0) wake_strong(b2);
+                    }
+                    remove_at(k);
+                    have = false;
+                }
+                if (have) ++k;
+                if (modified && ov) {
+                    if (ncand < S) cand[ncand++] = p;
+                    else e.flags |= FLAG_OVERFLOW;
+                }
             }
         }
-        // 3. narrow phase; player pairs (capsule-cuboid) come first in pair order
+        // Narrow phase on "my i-th candidate": the lanes of a warp work on different pairs in
+        // lockstep. Player pairs (capsule-cuboid) sort first, block pairs (cuboid-cuboid) after.
         int k = 0;
-        for (; k < ncand && cand[k] < W.n_player_pairs; ++k) {
-            int p = cand[k];
+        int i = 0;
+#pragma unroll 1
+        for (; i < ncand && cand[i] < W.n_player_pairs; ++i) {
+            int p = cand[i];
+            while (k < e.count && pair_at(k) < p) ++k;
+            bool have = k < e.count && pair_at(k) == p;
+            int slot = have ? slot_at(k) : -1;
             int c2 = W.pair_c2[p];
-            int at = find(p);
-            int slot = at >= 0 ? slot_at(at) : -1;
             Manifold m;
-            if (slot >= 0) load_manifold(slot, m);
+            if (have) load_manifold(slot, m);
             else m.npts = 0;
-            Iso pos12 = inv_mul(body_pose(0), collider_pose(c2));
+            Iso pose1 = body_pose(0);
+            Iso pos12 = inv_mul(pose1, collider_pose(c2));
             contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(W.hx[c2], W.hy[c2]), W.prediction);
-            commit(p, at, slot, m);
+            k = commit(p, k, have, slot, m, pose1);
         }
         if (NB > 1) {
-            for (; k < ncand; ++k) {
-                int p = cand[k];
+#pragma unroll 1
+            for (; i < ncand; ++i) {
+                int p = cand[i];
+                while (k < e.count && pair_at(k) < p) ++k;
+                bool have = k < e.count && pair_at(k) == p;
+                int slot = have ? slot_at(k) : -1;
                 int c1 = W.pair_c1[p], c2 = W.pair_c2[p];
-                int at = find(p);
-                int slot = at >= 0 ? slot_at(at) : -1;
                 Manifold m;
-                if (slot >= 0) load_manifold(slot, m);
+                if (have) load_manifold(slot, m);
                 else m.npts = 0;
-                Iso pos12 = inv_mul(collider_pose(c1), collider_pose(c2));
+                Iso pose1 = collider_pose(c1);
+                Iso pos12 = inv_mul(pose1, collider_pose(c2));
                 contact_cuboid_cuboid(m, pos12, V(W.hx[c1], W.hy[c1]), V(W.hx[c2], W.hy[c2]), W.prediction);
-                commit(p, at, slot, m);
+                k = commit(p, k, have, slot, m, pose1);
             }
         }
     }
-    // write a narrow-phase result back to the slot table. Only manifolds with points are kept:
-    // an empty manifold carries no state the next step can observe.
-    PRL_D void commit(int p, int at, int slot, const Manifold& m) {
+    // write a narrow-phase result back at sorted position k; returns the position after it. Only
+    // manifolds with points are kept: an empty one carries no state the next step can observe.
+    PRL_D int commit(int p, int k, bool have, int slot, const Manifold& m, const Iso& pose1) {
         if (m.npts > 0) {
-            if (slot < 0) slot = insert(p);
-            if (slot >= 0) store_manifold(slot, m);
-        } else if (at >= 0) {
-            remove_at(at);
+            if (!have) slot = insert_at(k);
+            if (slot >= 0) { store_manifold(slot, p, m, pose1); return k + 1; }
+            return k;
         }
+        if (have) remove_at(k);
+        return k;
     }
 
     // common.rs:175-195 distance_to_goals, editor pixels; +inf for a goal-less world
     PRL_D float distance_to_goals() const {
         float best = f32_inf();
+#pragma unroll 1
         for (int i = 0; i < W.n_goals; ++i) {
             v2 d = V(e.x[0] - W.gx[i], e.y[0] - W.gy[i]);
             float dx = fmaxf(fabsf(d.x * W.gxax[i] + d.y * W.gxay[i]) - W.ghw[i], 0.0f);
@@ -941,20 +972,16 @@ struct Stepper {
 
     // Environment::step (common.rs:215-340); returns distance_to_goals after the step
     PRL_D float step(uint32_t mv) {
-        for (int k = 0; k < e.count; ++k) solver_contacts(slot_at(k));
         player_move(mv);
         // first step only: every collider is new, so rapier detects collisions on the initial
         // poses before anything moves (SURVEY A.3 stage 1)
-        int pass = (e.flags & FLAG_FRESH) ? 0 : 1;
-        for (; pass < 2; ++pass) {
+#pragma unroll 1
+        for (int pass = (e.flags & FLAG_FRESH) ? 0 : 1; pass < 2; ++pass) {
             uint32_t moved = 0;
             if (pass == 1) moved = solve_and_integrate();
             detect_collisions(moved, pass == 0);
-            if (pass == 0) {
-                e.flags &= ~FLAG_FRESH;
-                for (int k = 0; k < e.count; ++k) solver_contacts(slot_at(k));
-            }
         }
+        e.flags &= ~FLAG_FRESH;
         // query_pipeline.update (common.rs:330-331) is never queried: omitted
         float d = distance_to_goals();
         if (!(e.flags & FLAG_WON) && W.n_goals > 0 && d < 1e-7f) e.flags |= FLAG_WON;

@@ -14,7 +14,7 @@
 
 namespace prl {
 
-constexpr int kBlock = 128;
+constexpr int kBlock = 64;
 
 __device__ __forceinline__ void stage_world(DevWorld* dst, const DevWorld* __restrict__ src) {
     static_assert(sizeof(DevWorld) % 16 == 0, "DevWorld is copied as 16-byte words");
@@ -59,16 +59,17 @@ __device__ __forceinline__ void env_load(const DevWorld& W, Env<NB>& e, const ui
             e.c[b] = 1.0f;
         }
     }
-    // live manifolds are stored compacted in pair order: slot k = k-th manifold
+    // live manifolds are stored compacted in pair order: slot k = k-th manifold. The 15 HBM
+    // words of a slot are the first 15 words of the 16-word thread-local record.
     int base = F_DYN + 8 * (W.n_bodies - 1);
     e.order = 0xfedcba9876543210ull;
-    e.used = e.count >= 32 ? ~0u : ((1u << e.count) - 1u);
+    e.used = (1u << e.count) - 1u;
+#pragma unroll 1
     for (int k = 0; k < e.count; ++k) {
         int f = base + MF_WORDS * k;
-        uint32_t h = st[(int64_t)f * n + i];
-        e.spair[k] = (int)(h & 0xffu);
-        e.snpts[k] = (int)(h >> 8);
-        for (int j = 0; j < 14; ++j) e.mf[k][j] = ld(f + 1 + j);
+        float* rec = &e.mf[k][0].x;
+#pragma unroll 1
+        for (int j = 0; j < MF_WORDS; ++j) rec[j] = ld(f + j);
     }
 }
 
@@ -88,11 +89,14 @@ __device__ __forceinline__ void env_store(const DevWorld& W, const Env<NB>& e, u
         }
     }
     int base = F_DYN + 8 * (W.n_bodies - 1);
+#pragma unroll 1
     for (int k = 0; k < count; ++k) {
         int slot = (int)((e.order >> (4 * k)) & 15u);
         int f = base + MF_WORDS * k;
-        st[(int64_t)f * n + i] = (uint32_t)e.spair[slot] | ((uint32_t)e.snpts[slot] << 8);
-        for (int j = 0; j < 14; ++j) sf(f + 1 + j, e.mf[slot][j]);
+        const float* rec = &e.mf[slot][0].x;
+        st[(int64_t)f * n + i] = __float_as_uint(rec[0]) & 0xfffu;  // pair | npts << 8 (solver-contact count is derived)
+#pragma unroll 1
+        for (int j = 1; j < MF_WORDS; ++j) sf(f + j, rec[j]);
     }
 }
 
@@ -132,6 +136,8 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const DevWorld* __restrict
     int steps = (int)st[(int64_t)F_STEPS * n + i];
     uint32_t mv = moves ? (moves[i] & 7u) : (uniform_move & 7u);
     Stepper<NB, MAXC> sim(W, e);
+    sim.refresh_solver_contacts();
+#pragma unroll 1
     for (int t = 0; t < n_steps; ++t) {
         float d = sim.step(mv);
         ++steps;
@@ -163,26 +169,30 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const DevWorld* __restr
     float score = __int_as_float(0x7f800000);
     int win_step = -1, steps = 0;
     const uint8_t* genome = genomes + i * (int64_t)genome_len;
-    bool stop = false;
-    for (int g = 0; g < genome_len && !stop; ++g) {
-        uint32_t mv = genome[g] & 7u;
-        for (int r = 0; r < repeat_move; ++r) {
-            float d = sim.step(mv);
-            ++steps;
-            score = fminf(score, d);
-            bool won = (e.flags & FLAG_WON) != 0;
-            if (won && win_step < 0) win_step = steps;
-            if (won && early_exit) { stop = true; break; }
-        }
-    }
-    int tail = number_of_steps % repeat_move;
-    for (int r = 0; r < tail; ++r) {
-        float d = sim.step(0u);
+    // one flat loop over the gene phase (genome_len x repeat_move steps) and the tail phase
+    // (number_of_steps % repeat_move default moves): a win in the gene phase skips to the tail,
+    // which then runs one more step before it sees won() -- the reference's two loops
+    const int main_steps = genome_len * repeat_move;
+    const int total = main_steps + number_of_steps % repeat_move;
+    int g = 0, rep = 0;
+    uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
+#pragma unroll 1
+    for (int t = 0; t < total;) {
+        const bool in_genes = t < main_steps;
+        float d = sim.step(in_genes ? gene : 0u);
         ++steps;
+        ++t;
         score = fminf(score, d);
         bool won = (e.flags & FLAG_WON) != 0;
         if (won && win_step < 0) win_step = steps;
-        if (won && early_exit) break;
+        if (in_genes && ++rep == repeat_move) {
+            rep = 0;
+            if (++g < genome_len) gene = genome[g] & 7u;
+        }
+        if (won && early_exit) {
+            if (!in_genes) break;
+            t = main_steps;
+        }
     }
     env_store(W, e, st, n, i);
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
