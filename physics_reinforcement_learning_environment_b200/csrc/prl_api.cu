@@ -40,13 +40,23 @@ int ensure_stage(void** buf, size_t* cap, size_t bytes) {
 
 inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
-// kernels are instantiated for 1 body (no pushable block), 2 bodies and the compiled maximum
-template <typename F1, typename F2, typename F5>
-void dispatch_bodies(int nb, F1 f1, F2 f2, F5 f5) {
-    if (nb == 1) f1();
-    else if (nb == 2) f2();
-    else f5();
+// Kernel variants: (bodies, world-table capacity). Small worlds (<= 15 blocks, the shipped
+// levels) with at most one pushable block get the compact tables and the 48-byte solver rows;
+// everything else runs the general variant.
+enum Variant { V1_SMALL, V2_SMALL, V1_BIG, VN_BIG };
+Variant pick_variant(const DevWorld& w) {
+    bool small = world_fits<DevWorldSmall>(w);
+    if (w.n_bodies == 1) return small ? V1_SMALL : V1_BIG;
+    if (w.n_bodies == 2 && small) return V2_SMALL;
+    return VN_BIG;
 }
+#define PRL_DISPATCH(variant, KERNEL, grid, stream, ...)                                                        \
+    switch (variant) {                                                                                           \
+        case V1_SMALL: KERNEL<1, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;               \
+        case V2_SMALL: KERNEL<2, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;               \
+        case V1_BIG: KERNEL<1, DevWorld><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;                      \
+        default: KERNEL<MAXB, DevWorld><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;                       \
+    }
 
 }  // namespace
 
@@ -189,12 +199,7 @@ int prl_batch_reset(prl_batch* b) {
 }
 
 static int launch_step(prl_batch* b, const uint8_t* dev_moves, uint32_t uniform, int n_steps) {
-    const int nb = b->host_world.n_bodies;
-    dispatch_bodies(
-        nb,
-        [&] { step_kernel<1><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dev_moves, uniform, n_steps); },
-        [&] { step_kernel<2><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dev_moves, uniform, n_steps); },
-        [&] { step_kernel<MAXB><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dev_moves, uniform, n_steps); });
+    PRL_DISPATCH(pick_variant(b->host_world), step_kernel, grid_for(b->n), b->stream, b->dev_world, b->state, b->n, dev_moves, uniform, n_steps);
     ++b->launches;
     CUDA_TRY(cudaGetLastError());
     return PRL_OK;
@@ -313,12 +318,8 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
     bool win_host = out_step_of_win && !is_device_ptr(out_step_of_win);
     float* ds = score_host ? nullptr : out_score;
     int32_t* dw = win_host ? nullptr : out_step_of_win;
-    const int nb = b->host_world.n_bodies;
-    dispatch_bodies(
-        nb,
-        [&] { rollout_kernel<1><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw); },
-        [&] { rollout_kernel<2><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw); },
-        [&] { rollout_kernel<MAXB><<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw); });
+    PRL_DISPATCH(pick_variant(b->host_world), rollout_kernel, grid_for(b->n), b->stream, b->dev_world, b->state, b->n, dg, genome_len,
+                 repeat_move, number_of_steps, early_exit, ds, dw);
     ++b->launches;
     CUDA_TRY(cudaGetLastError());
     // host outputs come straight from the state arrays the kernel also fills

@@ -28,8 +28,12 @@
 #if defined(__CUDACC__)
 #include <cuda_runtime.h>
 #define PRL_D __host__ __device__ __forceinline__
+// rarely taken paths are kept out of line: the step loop is instruction-fetch bound, so the hot
+// path should be as few cache lines as possible
+#define PRL_COLD static __host__ __device__ __noinline__
 #else
 #define PRL_D inline
+#define PRL_COLD static inline
 #endif
 
 namespace prl {
@@ -41,6 +45,30 @@ PRL_D int first_zero_bit(uint32_t used) {  // index of the lowest clear bit, 32 
 #else
     for (int i = 0; i < 32; ++i) if (!((used >> i) & 1u)) return i;
     return 32;
+#endif
+}
+// exclusive prefix sum of v over the lanes of the warp (all 32 lanes must call it); the host
+// build is a single "lane"
+PRL_D int warp_exclusive_sum(int v, int& total) {
+#if defined(__CUDA_ARCH__)
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)(threadIdx.x & 31u) >= o) incl += up;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    return incl - v;
+#else
+    total = v;
+    return 0;
+#endif
+}
+PRL_D bool warp_all(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __all_sync(0xffffffffu, p) != 0;
+#else
+    return p;
 #endif
 }
 PRL_D float f32_inf() {
@@ -203,8 +231,7 @@ PRL_D float cuboid_sat_oneway(v2 he1, v2 he2, const Iso& pos12, v2& best_dir) {
 }
 
 // parry contact_manifold_cuboid_cuboid
-PRL_D void contact_cuboid_cuboid(Manifold& m, const Iso& pos12, v2 he1, v2 he2, float prediction) {
-    if (manifold_try_update(m, pos12)) return;
+PRL_COLD void contact_cuboid_cuboid_full(Manifold& m, const Iso& pos12, v2 he1, v2 he2, float prediction) {
     Iso pos21 = inverse(pos12);
     v2 d1, d2;
     float sep1 = cuboid_sat_oneway(he1, he2, pos12, d1);
@@ -280,8 +307,7 @@ PRL_D bool segment_box_closest(v2 a, v2 b, v2 he, float& u_out, v2& q_out) {
 
 // parry contact_manifold_pfm_pfm with pfm1 = the capsule's segment (border radius r) and
 // pfm2 = the cuboid: closest points, then segment-vs-support-face clipping, then the radius shift.
-PRL_D void contact_capsule_cuboid(Manifold& m, const Iso& pos12, float radius, float hh, v2 he2, float prediction) {
-    if (manifold_try_update(m, pos12)) return;
+PRL_COLD void contact_capsule_cuboid_full(Manifold& m, const Iso& pos12, float radius, float hh, v2 he2, float prediction) {
     const float total_prediction = prediction + radius + 0.0f;
     v2 sa = V(0.0f, -hh), sb = V(0.0f, hh);
     v2 a2 = xform_inv(pos12, sa), b2 = xform_inv(pos12, sb);
@@ -333,6 +359,14 @@ PRL_D void contact_capsule_cuboid(Manifold& m, const Iso& pos12, float radius, f
     }
     m.n1 = dir;
     m.n2 = n2;
+}
+
+// hot path of both contact routines: the cached manifold usually survives (persistence first)
+PRL_D void contact_cuboid_cuboid(Manifold& m, const Iso& pos12, v2 he1, v2 he2, float prediction) {
+    if (!manifold_try_update(m, pos12)) contact_cuboid_cuboid_full(m, pos12, he1, he2, prediction);
+}
+PRL_D void contact_capsule_cuboid(Manifold& m, const Iso& pos12, float radius, float hh, v2 he2, float prediction) {
+    if (!manifold_try_update(m, pos12)) contact_capsule_cuboid_full(m, pos12, radius, hh, he2, prediction);
 }
 
 // sin and cos of a pushable block's rotation increment; kept out of line so the pose update of
@@ -392,6 +426,8 @@ struct Env {
     uint64_t order;      // nibble k = slot of the k-th live manifold in ascending pair order
     int count;
     uint32_t used;       // bit s = slot s is live
+    uint64_t spair[2];   // byte s = pair index of slot s (registers: the lists are walked every stage)
+    uint32_t sns;        // 2 bits per slot: number of solver contacts of slot s
     // mf[s]: the cached contact manifold of one collider pair
     //   [0] = (hdr, n1.x, n1.y, n2.x)      hdr bits = pair | npts << 8 | n_solver_contacts << 12
     //   [1] = (n2.y, p1a.x, p1a.y, p2a.x)
@@ -401,26 +437,56 @@ struct Env {
     // sc[s]: its solver contacts (world space), refreshed whenever the narrow phase visits the pair
     //   [0] = (normal.x, normal.y, pt0.x, pt0.y)   [1] = (dist0, pt1.x, pt1.y, dist1)
     f4 sc[S][2];
-    // velocity-constraint rows, one per solver contact, in Gauss-Seidel order (per-step scratch)
-    //   [0] = (dir.x, dir.y, inv_mass1, inv_mass2)
-    //   [1] = (gcross1, gcross2, cfm_factor, bodies)   bodies bits = body1 | body2 << 8
-    //   [2] = (rhs, r, impulse, tangent impulse)
-    //   [3] = (t_gcross1, t_gcross2, t_rhs, t_r)
-    f4 row[2 * S][4];
-    float rhs_wo_bias[2 * S];
 };
 
-template <int NB, int S>
+template <int NB, int S, class WT = DevWorld>
 struct Stepper {
     using E = Env<NB, S>;
     static constexpr int kGround = NB;  // pseudo body index of the fixed world: zero velocity, zero inverse mass
-    const DevWorld& W;
+    // Velocity-constraint rows, one per solver contact, in Gauss-Seidel order (per-step scratch),
+    // as 16-byte quads:
+    //   quad 0 = (dir.x, dir.y, gcross2, t_gcross2)
+    //   quad 1 = (rhs, r, normal impulse, tangent impulse)
+    //   quad 2 = (t_rhs, t_r, rhs_wo_bias, bodies)   bodies bits = body1 | body2 << 8 | fast << 16
+    //   quad 3 = (gcross1, t_gcross1, -, -)          body 1's angular terms, two-body rows only
+    // With at most one pushable block (NB <= 2) the only two-body rows are the <= 2 rows of the
+    // player-block manifold, whose quad 3 stays in registers (tb_g1 / tb_tg1): rows are 48 bytes.
+    // The 14 solver sweeps re-read every row and their working set per SM exceeds L1, so rows
+    // live in shared memory: each warp owns a pool of `pool_rows` rows (kRowQuads planes of
+    // quads, XOR-swizzled against bank conflicts), handed out every step by a warp prefix sum
+    // over the lanes' row counts -- the average environment needs far fewer rows than the worst
+    // case. If a warp's rows do not all fit, its lanes solve in rounds (see the kernels).
+    static constexpr int kRowQuads = NB <= 2 ? 3 : 4;
+    static constexpr int kMaxRows = 2 * S;  // rows one environment can need; pool_rows must be >= this
+    const WT& W;
     E& e;
-    PRL_D Stepper(const DevWorld& w, E& env) : W(w), e(env) {}
+    f4* pool;
+    int pool_rows;
+    int rbase;          // first pool row of this lane, this step
+    float tb_g1[2], tb_tg1[2];
+    // constraint selection of the current step (begin_step -> finish_step)
+    uint32_t active;
+    uint64_t cons;      // nibble i = slot of my i-th constraint
+    int ncons, need, ntb;   // constraints, rows, two-body rows (the head of the row list)
+    // collision detection owed for the poses of the last position update (detect_pending)
+    uint32_t pend_moved;
+    bool pend_all, first_step;
+    PRL_D Stepper(const WT& w, E& env, f4* warp_pool, int warp_pool_rows)
+        : W(w), e(env), pool(warp_pool), pool_rows(warp_pool_rows), rbase(0), active(0), cons(0), ncons(0), need(0), ntb(0), pend_moved(0),
+          pend_all((env.flags & FLAG_FRESH) != 0), first_step(false) {
+        tb_g1[0] = tb_g1[1] = tb_tg1[0] = tb_tg1[1] = 0.0f;
+    }
+    // quad q of my row j is row_ptr(j)[q * pool_rows]
+    PRL_D f4* row_ptr(int j) const {
+        int g = rbase + j;
+        return pool + (g ^ ((g >> 3) & 7));
+    }
+    PRL_D int row_qstride() const { return pool_rows; }
 
     PRL_D int slot_at(int k) const { return (int)((e.order >> (4 * k)) & 15u); }
-    PRL_D uint32_t hdr(int slot) const { return f32_bits(e.mf[slot][0].x); }
-    PRL_D int pair_at(int k) const { return (int)(hdr(slot_at(k)) & 0xffu); }
+    PRL_D int pair_of(int slot) const { return (int)(((slot < 8 ? e.spair[0] : e.spair[1]) >> (8 * (slot & 7))) & 0xffu); }
+    PRL_D int ns_of(int slot) const { return (int)((e.sns >> (2 * slot)) & 3u); }
+    PRL_D int pair_at(int k) const { return pair_of(slot_at(k)); }
     PRL_D Iso body_pose(int b) const { Iso p; p.t = V(sel(e.x, b), sel(e.y, b)); p.c = sel(e.c, b); p.s = sel(e.s, b); return p; }
     PRL_D Iso collider_pose(int c) const {
         int b = W.body_of[c];
@@ -456,7 +522,13 @@ struct Stepper {
             }
         }
         f4 a, b, c, d;
-        a.x = bits_f32((uint32_t)pair | ((uint32_t)m.npts << 8) | ((uint32_t)ns << 12));
+        a.x = bits_f32((uint32_t)pair | ((uint32_t)m.npts << 8));
+        e.sns = (e.sns & ~(3u << (2 * slot))) | ((uint32_t)ns << (2 * slot));
+        {
+            uint64_t sh = 8 * (slot & 7);
+            if (slot < 8) e.spair[0] = (e.spair[0] & ~(0xffull << sh)) | ((uint64_t)pair << sh);
+            else e.spair[1] = (e.spair[1] & ~(0xffull << sh)) | ((uint64_t)pair << sh);
+        }
         a.y = m.n1.x; a.z = m.n1.y; a.w = m.n2.x;
         b.x = m.n2.y; b.y = m.p1[0].x; b.z = m.p1[0].y; b.w = m.p2[0].x;
         c.x = m.p2[0].y; c.y = m.dist[0]; c.z = m.p1[1].x; c.w = m.p1[1].y;
@@ -475,7 +547,7 @@ struct Stepper {
             int slot = slot_at(k);
             Manifold m;
             load_manifold(slot, m);
-            int p = (int)(hdr(slot) & 0xffu);
+            int p = (int)(f32_bits(e.mf[slot][0].x) & 0xffu);
             store_manifold(slot, p, m, collider_pose(W.pair_c1[p]));
         }
     }
@@ -530,8 +602,7 @@ struct Stepper {
 #pragma unroll 1
         for (int k = 0; k < e.count; ++k) {
             int slot = slot_at(k);
-            uint32_t h = hdr(slot);
-            int p = (int)(h & 0xffu), ns = (int)(h >> 12);
+            int p = pair_of(slot), ns = ns_of(slot);
             if (p >= W.n_player_pairs) break;
             ++nplayer;
             int body = W.body_of[W.pair_c2[p]];
@@ -571,9 +642,8 @@ struct Stepper {
 #pragma unroll 1
             for (int k = 0; k < nplayer; ++k) {
                 int slot = slot_at(k);
-                uint32_t h = hdr(slot);
-                int ns = (int)(h >> 12);
-                int body = W.body_of[W.pair_c2[h & 0xffu]];
+                int ns = ns_of(slot);
+                int body = W.body_of[W.pair_c2[pair_of(slot)]];
                 f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
 #pragma unroll 1
                 for (int i = 0; i < ns; ++i) {
@@ -618,9 +688,9 @@ struct Stepper {
                 for (int round = 0; round < NB - 1; ++round) {
 #pragma unroll 1
                     for (int k = 0; k < e.count; ++k) {
-                        uint32_t h = hdr(slot_at(k));
-                        if ((h >> 12) == 0) continue;
-                        int p = (int)(h & 0xffu);
+                        int slot = slot_at(k);
+                        if (ns_of(slot) == 0) continue;
+                        int p = pair_of(slot);
                         int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
                         if (b1 < 0 || b2 < 0) continue;
                         uint32_t m1 = 1u << b1, m2 = 1u << b2;
@@ -645,8 +715,7 @@ struct Stepper {
     // two-body row against the pseudo body kGround (zero velocity, zero inverse mass, zero
     // angular response), which evaluates to the same values as rapier's ground formulas.
     PRL_D int generate_constraint(int slot, int nrows) {
-        uint32_t h = hdr(slot);
-        int p = (int)(h & 0xffu), ns = (int)(h >> 12);
+        int p = pair_of(slot), ns = ns_of(slot);
         int h1 = W.body_of[W.pair_c1[p]], h2 = W.body_of[W.pair_c2[p]];
         bool two_body = h1 >= 0 && h2 >= 0;
         f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
@@ -669,7 +738,7 @@ struct Stepper {
             ccd = W.ccd_thickness[h1] + W.ccd_thickness[h2];
         }
         v2 tan1 = V(-dir1.y, dir1.x);
-        float bodies = bits_f32((uint32_t)(two_body ? h1 : kGround) | ((uint32_t)h2 << 8));
+        uint32_t bodies = (uint32_t)(two_body ? h1 : kGround) | ((uint32_t)h2 << 8);
         bool fast = false;
 #pragma unroll 1
         for (int k = 0; k < ns; ++k) {
@@ -706,96 +775,155 @@ struct Stepper {
                 tr = dot(tan1, tan1 * im2) + t_gcross2 * t_gcross2;
             }
             v2 dv = (vel1 - vel2) + V(0.0f, 0.0f);
-            r0.x = dir1.x; r0.y = dir1.y; r0.z = im1; r0.w = im2;
-            r1.x = gcross1; r1.y = gcross2; r1.z = W.cfm_factor; r1.w = bodies;
-            r2.x = rhs; r2.y = pm; r2.z = 0.0f; r2.w = 0.0f;
-            r3.x = t_gcross1; r3.y = t_gcross2; r3.z = dot(dv, tan1); r3.w = inv0(tr);
+            r0.x = dir1.x; r0.y = dir1.y; r0.z = gcross2; r0.w = t_gcross2;
+            r1.x = rhs; r1.y = pm; r1.z = 0.0f; r1.w = 0.0f;
+            r2.x = dot(dv, tan1); r2.y = inv0(tr); r2.z = rhs_wo_bias; r2.w = bits_f32(bodies);
             int j = nrows + k;
-            e.row[j][0] = r0; e.row[j][1] = r1; e.row[j][2] = r2; e.row[j][3] = r3;
-            e.rhs_wo_bias[j] = rhs_wo_bias;
+            f4* rp = row_ptr(j);
+            int qs = row_qstride();
+            rp[0] = r0; rp[qs] = r1; rp[2 * qs] = r2;
+            if (kRowQuads == 4) {
+                r3.x = gcross1; r3.y = t_gcross1; r3.z = 0.0f; r3.w = 0.0f;
+                rp[3 * qs] = r3;
+            } else if (NB == 2 && two_body) {
+                if (j == 0) { tb_g1[0] = gcross1; tb_tg1[0] = t_gcross1; }
+                else { tb_g1[1] = gcross1; tb_tg1[1] = t_gcross1; }
+            }
         }
         if (fast) {  // a fast contact makes the whole constraint rigid (cfm_factor 1)
 #pragma unroll 1
-            for (int k = 0; k < ns; ++k) e.row[nrows + k][1].z = 1.0f;
+            for (int k = 0; k < ns; ++k) row_ptr(nrows + k)[2 * row_qstride()].w = bits_f32(bodies | (1u << 16));
         }
         return nrows + ns;
     }
 
-    // One Gauss-Seidel row update: rapier VelocityConstraintElement::solve_group, normal part or
-    // friction part. Ground rows use body1 = kGround, whose increments stay zero.
-    PRL_D void solve_row(int j, bool normal_part, float (&dlx)[NB + 1], float (&dly)[NB + 1], float (&da)[NB + 1]) {
-        f4 r0 = e.row[j][0], r2 = e.row[j][2];
-        v2 dir1 = V(r0.x, r0.y);
-        float im1 = r0.z, im2 = r0.w;
-        if (normal_part) {
-            f4 r1 = e.row[j][1];
-            uint32_t bodies = f32_bits(r1.w);
-            int b1 = (int)(bodies & 0xffu), b2 = (int)(bodies >> 8);
-            v2 l1 = V(sel(dlx, b1), sel(dly, b1)), l2 = V(sel(dlx, b2), sel(dly, b2));
-            float a1 = sel(da, b1), a2 = sel(da, b2);
-            float dvel = dot(dir1, l1) + r1.x * a1 - dot(dir1, l2) + r1.y * a2 + r2.x;
-            float ni = r1.z * fmaxf(r2.z - r2.y * dvel, 0.0f);
-            float dl = ni - r2.z;
-            e.row[j][2].z = ni;
-            l1 = l1 + (dir1 * im1) * dl;
-            a1 += r1.x * dl;
-            l2 = l2 + (dir1 * im2) * -dl;
-            a2 += r1.y * dl;
-            if (NB > 1) { put(dlx, b1, l1.x); put(dly, b1, l1.y); put(da, b1, a1); }
-            put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
+    // Gauss-Seidel row updates: rapier VelocityConstraintElement::solve_group (two bodies) and
+    // VelocityGroundConstraintElement::solve_group (one body), normal part and friction part.
+    // Two-body rows come first in the row list (ntb of them), ground rows after. The body
+    // increments dl* stay in registers: with one pushable block (NB == 2) a two-body row is
+    // always (player, block) and a ground row selects one of two bodies.
+    template <bool NORMAL>
+    PRL_D void ground_row(int j, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+        f4* rp = row_ptr(j);
+        const int qs = pool_rows;
+        f4 r0 = rp[0], r1 = rp[qs];
+        v2 dir = V(r0.x, r0.y);
+        float g2, rhs, rr, acc;
+        uint32_t bodies;
+        if (NORMAL) {
+            g2 = r0.z; rr = r1.y; acc = r1.z;
+            if (biased) { rhs = r1.x; bodies = f32_bits(rp[2 * qs].w); }
+            else { f4 r2 = rp[2 * qs]; rhs = r2.z; bodies = f32_bits(r2.w); }
         } else {
-            f4 r3 = e.row[j][3];
-            uint32_t bodies = f32_bits(e.row[j][1].w);
-            int b1 = (int)(bodies & 0xffu), b2 = (int)(bodies >> 8);
-            v2 tan1 = V(-dir1.y, dir1.x);
-            v2 l1 = V(sel(dlx, b1), sel(dly, b1)), l2 = V(sel(dlx, b2), sel(dly, b2));
-            float a1 = sel(da, b1), a2 = sel(da, b2);
-            float limit = kFriction * r2.z;
-            float dvel = dot(tan1, l1) + r3.x * a1 - dot(tan1, l2) + r3.y * a2 + r3.z;
-            float ni = fminf(fmaxf(r2.w - r3.w * dvel, -limit), limit);
-            float dl = ni - r2.w;
-            e.row[j][2].w = ni;
-            l1 = l1 + (tan1 * im1) * dl;
-            a1 += r3.x * dl;
-            l2 = l2 + (tan1 * im2) * -dl;
-            a2 += r3.y * dl;
-            if (NB > 1) { put(dlx, b1, l1.x); put(dly, b1, l1.y); put(da, b1, a1); }
-            put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
+            f4 r2 = rp[2 * qs];
+            dir = V(-dir.y, dir.x);  // tangent
+            g2 = r0.w; rhs = r2.x; rr = r2.y; acc = r1.w;
+            bodies = f32_bits(r2.w);
         }
+        int b2 = (int)((bodies >> 8) & 0xffu);
+        float im2 = W.inv_mass[b2];
+        v2 l2 = V(sel(dlx, b2), sel(dly, b2));
+        float a2 = sel(da, b2);
+        float dvel = -dot(dir, l2) + g2 * a2 + rhs;
+        float ni;
+        if (NORMAL) {
+            // the stabilisation sweep runs without the penetration bias and without softness
+            float cfm = (biased && !(bodies >> 16)) ? W.cfm_factor : 1.0f;
+            ni = cfm * fmaxf(acc - rr * dvel, 0.0f);
+            rp[qs].z = ni;
+        } else {
+            float limit = kFriction * r1.z;
+            ni = fminf(fmaxf(acc - rr * dvel, -limit), limit);
+            rp[qs].w = ni;
+        }
+        float dl = ni - acc;
+        l2 = l2 + (dir * im2) * -dl;
+        a2 += g2 * dl;
+        put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
+    }
+    template <bool NORMAL>
+    PRL_D void two_body_row(int j, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+        f4* rp = row_ptr(j);
+        const int qs = pool_rows;
+        f4 r0 = rp[0], r1 = rp[qs], r2 = rp[2 * qs];
+        v2 dir = V(r0.x, r0.y);
+        uint32_t bodies = f32_bits(r2.w);
+        int b1 = NB == 2 ? 0 : (int)(bodies & 0xffu), b2 = NB == 2 ? 1 : (int)((bodies >> 8) & 0xffu);
+        float im1 = W.inv_mass[b1], im2 = W.inv_mass[b2];
+        float g1, g2, rhs, rr, acc;
+        if (kRowQuads == 4) { f4 r3 = rp[3 * qs]; g1 = NORMAL ? r3.x : r3.y; }
+        else g1 = NORMAL ? (j == 0 ? tb_g1[0] : tb_g1[1]) : (j == 0 ? tb_tg1[0] : tb_tg1[1]);
+        if (NORMAL) { g2 = r0.z; rr = r1.y; acc = r1.z; rhs = biased ? r1.x : r2.z; }
+        else { dir = V(-dir.y, dir.x); g2 = r0.w; rhs = r2.x; rr = r2.y; acc = r1.w; }
+        v2 l1 = V(sel(dlx, b1), sel(dly, b1)), l2 = V(sel(dlx, b2), sel(dly, b2));
+        float a1 = sel(da, b1), a2 = sel(da, b2);
+        float dvel = dot(dir, l1) + g1 * a1 - dot(dir, l2) + g2 * a2 + rhs;
+        float ni;
+        if (NORMAL) {
+            float cfm = (biased && !(bodies >> 16)) ? W.cfm_factor : 1.0f;
+            ni = cfm * fmaxf(acc - rr * dvel, 0.0f);
+            rp[qs].z = ni;
+        } else {
+            float limit = kFriction * r1.z;
+            ni = fminf(fmaxf(acc - rr * dvel, -limit), limit);
+            rp[qs].w = ni;
+        }
+        float dl = ni - acc;
+        l1 = l1 + (dir * im1) * dl;
+        a1 += g1 * dl;
+        l2 = l2 + (dir * im2) * -dl;
+        a2 += g2 * dl;
+        put(dlx, b1, l1.x); put(dly, b1, l1.y); put(da, b1, a1);
+        put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
     }
 
-    // rapier islands + constraint build + VelocitySolver::solve + position update for the
-    // active bodies (SURVEY A.3 stages 2-7). Returns the mask of bodies that moved.
-    PRL_D uint32_t solve_and_integrate() {
+    // rapier IslandManager::update_active_set_with_contacts + NarrowPhase::select_active_contacts:
+    // which manifolds become constraints this step -- two-body manifolds first, then one-body
+    // ("ground") ones, each in pair order -- and how many rows they need.
+    PRL_D void select_constraints() {
         update_active_set();
-        uint32_t active = ~e.sleeping & ((1u << W.n_bodies) - 1u);
-        // constraint rows: two-body manifolds first, then one-body ("ground") ones, each in pair order
-        int nrows = 0;
+        active = ~e.sleeping & ((1u << W.n_bodies) - 1u);
+        cons = 0;
+        ncons = 0;
+        need = 0;
+        ntb = 0;
 #pragma unroll 1
         for (int pass = NB == 1 ? 1 : 0; pass < 2; ++pass) {
 #pragma unroll 1
             for (int k = 0; k < e.count; ++k) {
                 int slot = slot_at(k);
-                uint32_t h = hdr(slot);
-                if ((h >> 12) == 0) continue;
-                int p = (int)(h & 0xffu);
+                int ns = ns_of(slot);
+                if (ns == 0) continue;
+                int p = pair_of(slot);
                 int h1 = W.body_of[W.pair_c1[p]], h2 = W.body_of[W.pair_c2[p]];
                 bool two_body = h1 >= 0 && h2 >= 0;
                 if ((pass == 0) != two_body) continue;
                 bool awake1 = h1 >= 0 && ((active >> h1) & 1u);
                 bool awake2 = h2 >= 0 && ((active >> h2) & 1u);
                 if (!awake1 && !awake2) continue;
-                nrows = generate_constraint(slot, nrows);
+                cons |= (uint64_t)slot << (4 * ncons);
+                ++ncons;
+                need += ns;
+                if (two_body) ntb += ns;
             }
         }
-        float dlx[NB + 1], dly[NB + 1], da[NB + 1];
+    }
+
+    // constraint build + VelocitySolver::solve + position update for the active bodies (SURVEY
+    // A.3 stages 4-7), with this lane's rows starting at pool row `base`. Returns the mask of
+    // bodies that moved.
+    PRL_D uint32_t solve_and_integrate(int base) {
+        rbase = base;
+        int nrows = 0;
+#pragma unroll 1
+        for (int i = 0; i < ncons; ++i) nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows);
+        float dlx[NB], dly[NB], da[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             dlx[b] = b < W.n_bodies ? W.gdv_x[b] : 0.0f;
             dly[b] = b < W.n_bodies ? W.gdv_y[b] : 0.0f;
             da[b] = 0.0f;
         }
-        dlx[NB] = 0.0f; dly[NB] = 0.0f; da[NB] = 0.0f;
         float nx[NB], ny[NB], nc[NB], ns[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) { nx[b] = e.x[b]; ny[b] = e.y[b]; nc[b] = e.c[b]; ns[b] = e.s[b]; }
@@ -814,13 +942,23 @@ struct Stepper {
                         nx[b] = np.t.x; ny[b] = np.t.y; nc[b] = np.c; ns[b] = np.s;
                     }
                 }
-                // the stabilisation sweep runs without the penetration bias and without softness
-#pragma unroll 1
-                for (int j = 0; j < nrows; ++j) { e.row[j][2].x = e.rhs_wo_bias[j]; e.row[j][1].z = 1.0f; }
             }
-            bool normal_part = sweep == 12 || (sweep < 8 && (sweep & 1) == 0);
+            const bool biased = sweep < 12;
+            if (sweep == 12 || (sweep < 8 && (sweep & 1) == 0)) {
+                if (NB > 1) {
 #pragma unroll 1
-            for (int j = 0; j < nrows; ++j) solve_row(j, normal_part, dlx, dly, da);
+                    for (int j = 0; j < ntb; ++j) two_body_row<true>(j, biased, dlx, dly, da);
+                }
+#pragma unroll 1
+                for (int j = NB > 1 ? ntb : 0; j < nrows; ++j) ground_row<true>(j, biased, dlx, dly, da);
+            } else {
+                if (NB > 1) {
+#pragma unroll 1
+                    for (int j = 0; j < ntb; ++j) two_body_row<false>(j, biased, dlx, dly, da);
+                }
+#pragma unroll 1
+                for (int j = NB > 1 ? ntb : 0; j < nrows; ++j) ground_row<false>(j, biased, dlx, dly, da);
+            }
         }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -882,7 +1020,7 @@ struct Stepper {
         // list: a pair that left the broad phase drops its manifold (NarrowPhase::remove_pair wakes
         // both bodies if it had an active contact); an overlapping pair with a moved collider
         // becomes a narrow-phase candidate.
-        int cand[S];
+        uint64_t cand[2] = {0ull, 0ull};  // byte i = pair index of my i-th candidate
         int ncand = 0;
         {
             int k = 0;  // position in the sorted manifold list of the first entry with pair >= p
@@ -892,7 +1030,7 @@ struct Stepper {
                 bool ov = pair_overlaps(p, moved, all, bmnx, bmny, bmxx, bmxy, modified);
                 bool have = k < e.count && pair_at(k) == p;
                 if (modified && !ov && have) {
-                    if ((hdr(slot_at(k)) >> 12) != 0) {
+                    if (ns_of(slot_at(k)) != 0) {
                         int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
                         if (b1 >= 0) wake_strong(b1);
                         if (b2 >= 0) wake_strong(b2);
@@ -902,7 +1040,11 @@ struct Stepper {
                 }
                 if (have) ++k;
                 if (modified && ov) {
-                    if (ncand < S) cand[ncand++] = p;
+                    if (ncand < 16) {
+                        if (ncand < 8) cand[0] |= (uint64_t)p << (8 * ncand);
+                        else cand[1] |= (uint64_t)p << (8 * (ncand - 8));
+                        ++ncand;
+                    }
                     else e.flags |= FLAG_OVERFLOW;
                 }
             }
@@ -911,9 +1053,10 @@ struct Stepper {
         // lockstep. Player pairs (capsule-cuboid) sort first, block pairs (cuboid-cuboid) after.
         int k = 0;
         int i = 0;
+        auto cand_at = [&](int q) { return (int)(((q < 8 ? cand[0] : cand[1]) >> (8 * (q & 7))) & 0xffu); };
 #pragma unroll 1
-        for (; i < ncand && cand[i] < W.n_player_pairs; ++i) {
-            int p = cand[i];
+        for (; i < ncand && cand_at(i) < W.n_player_pairs; ++i) {
+            int p = cand_at(i);
             while (k < e.count && pair_at(k) < p) ++k;
             bool have = k < e.count && pair_at(k) == p;
             int slot = have ? slot_at(k) : -1;
@@ -929,7 +1072,7 @@ struct Stepper {
         if (NB > 1) {
 #pragma unroll 1
             for (; i < ncand; ++i) {
-                int p = cand[i];
+                int p = cand_at(i);
                 while (k < e.count && pair_at(k) < p) ++k;
                 bool have = k < e.count && pair_at(k) == p;
                 int slot = have ? slot_at(k) : -1;
@@ -970,22 +1113,49 @@ struct Stepper {
         return best;
     }
 
-    // Environment::step (common.rs:215-340); returns distance_to_goals after the step
-    PRL_D float step(uint32_t mv) {
-        player_move(mv);
-        // first step only: every collider is new, so rapier detects collisions on the initial
-        // poses before anything moves (SURVEY A.3 stage 1)
-#pragma unroll 1
-        for (int pass = (e.flags & FLAG_FRESH) ? 0 : 1; pass < 2; ++pass) {
-            uint32_t moved = 0;
-            if (pass == 1) moved = solve_and_integrate();
-            detect_collisions(moved, pass == 0);
+    // Environment::step (common.rs:215-340) in three parts, so that the collision detection has
+    // one call site and the warp can hand out the solver's row pool between the halves (every
+    // lane of the warp takes part in that hand-out, including lanes whose rollout has ended):
+    //
+    //   detect_pending();                 // broad + narrow phase owed by the previous position update
+    //   need = begin_step(move);          // ground scan + move impulses + constraint selection
+    //   base = warp_exclusive_sum(need);  // (kernel) rows from the warp's pool
+    //   d = finish_step(base);            // solve, integrate, win latch
+    //
+    // rapier runs the detection at the END of PhysicsPipeline::step; running it at the start of
+    // the next step (and once more after the last one) is the same sequence of operations.
+    PRL_D void detect_pending() {
+        if (pend_all || pend_moved != 0) {
+            // first step only: every collider is new, so rapier detects collisions on the initial
+            // poses before anything moves (SURVEY A.3 stage 1) -- but Environment::step's ground
+            // scan ran before that and saw no contacts (common.rs:224)
+            first_step = pend_all;
+            detect_collisions(pend_moved, pend_all);
+            pend_all = false;
+            pend_moved = 0;
+            e.flags &= ~FLAG_FRESH;
         }
-        e.flags &= ~FLAG_FRESH;
+    }
+    PRL_D int begin_step(uint32_t mv) {
+        if (!first_step) player_move(mv);
+        first_step = false;
+        select_constraints();
+        return need;
+    }
+    PRL_D float finish_step(int base) {
+        pend_moved = solve_and_integrate(base);
         // query_pipeline.update (common.rs:330-331) is never queried: omitted
         float d = distance_to_goals();
         if (!(e.flags & FLAG_WON) && W.n_goals > 0 && d < 1e-7f) e.flags |= FLAG_WON;
         return d;
+    }
+    // the whole step for one lane on its own (host build); call detect_pending() once more after
+    // the last step
+    PRL_D float step(uint32_t mv) {
+        detect_pending();
+        int want = begin_step(mv), total;
+        int base = warp_exclusive_sum(want, total);
+        return finish_step(base);
     }
 };
 

@@ -15,17 +15,46 @@
 namespace prl {
 
 constexpr int kBlock = 64;
+// Shared-memory budget of a 64-thread block: the world tables plus one pool of velocity-constraint
+// rows per warp (prl_device.cuh, Stepper). A 65536-environment batch puts 7 blocks on each SM, so
+// a block may use 227 KB / 7 = 32.4 KB: 15 KB of rows per warp beside the 1 KB tables of a small
+// world (320 rows of 48 B), 12 KB beside the 6.1 KB full-size tables.
+template <class WT> struct PoolBytes { static constexpr int value = 12288; };
+template <> struct PoolBytes<DevWorldSmall> { static constexpr int value = 15360; };
 
-__device__ __forceinline__ void stage_world(DevWorld* dst, const DevWorld* __restrict__ src) {
-    static_assert(sizeof(DevWorld) % 16 == 0, "DevWorld is copied as 16-byte words");
-    const uint4* s = reinterpret_cast<const uint4*>(src);
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    for (int i = threadIdx.x; i < (int)(sizeof(DevWorld) / 16); i += blockDim.x) d[i] = s[i];
+// block-wide copy of the world tables into shared memory (compacting into WT's capacities)
+template <class WT>
+__device__ __forceinline__ void stage_world(WT* dst, const DevWorld* __restrict__ src) {
+    const int t = threadIdx.x, nt = blockDim.x;
+    if (t == 0) {
+        dst->n_colliders = src->n_colliders; dst->n_bodies = src->n_bodies; dst->n_pairs = src->n_pairs; dst->n_goals = src->n_goals;
+        dst->n_player_pairs = src->n_player_pairs; dst->n_slots = src->n_slots;
+        dst->radius = src->radius; dst->half_height = src->half_height; dst->lower_off = src->lower_off;
+        dst->dt = src->dt; dst->inv_dt = src->inv_dt; dst->erp_inv_dt = src->erp_inv_dt; dst->cfm_factor = src->cfm_factor;
+        dst->prediction = src->prediction; dst->allowed_linear_error = src->allowed_linear_error; dst->aabb_margin = src->aabb_margin;
+        dst->scale = src->scale;
+    }
+    for (int c = t; c < src->n_colliders; c += nt) {
+        dst->cx[c] = src->cx[c]; dst->cy[c] = src->cy[c]; dst->cc[c] = src->cc[c]; dst->cs[c] = src->cs[c];
+        dst->hx[c] = src->hx[c]; dst->hy[c] = src->hy[c];
+        dst->amnx[c] = src->amnx[c]; dst->amny[c] = src->amny[c]; dst->amxx[c] = src->amxx[c]; dst->amxy[c] = src->amxy[c];
+        dst->body_of[c] = src->body_of[c];
+    }
+    for (int b = t; b < MAXB; b += nt) {
+        dst->inv_mass[b] = src->inv_mass[b]; dst->inv_inertia_sqrt[b] = src->inv_inertia_sqrt[b];
+        dst->ccd_thickness[b] = src->ccd_thickness[b]; dst->gdv_x[b] = src->gdv_x[b]; dst->gdv_y[b] = src->gdv_y[b];
+        dst->collider_of[b] = src->collider_of[b];
+    }
+    for (int p = t; p < src->n_pairs; p += nt) { dst->pair_c1[p] = src->pair_c1[p]; dst->pair_c2[p] = src->pair_c2[p]; }
+    for (int g = t; g < src->n_goals; g += nt) {
+        dst->gx[g] = src->gx[g]; dst->gy[g] = src->gy[g]; dst->ghw[g] = src->ghw[g]; dst->ghh[g] = src->ghh[g];
+        dst->gxax[g] = src->gxax[g]; dst->gxay[g] = src->gxay[g]; dst->gyax[g] = src->gyax[g]; dst->gyay[g] = src->gyay[g];
+    }
     __syncthreads();
 }
 
-template <int NB>
-__device__ __forceinline__ void env_init(const DevWorld& W, Env<NB>& e) {
+template <int NB, class WT>
+__device__ __forceinline__ void env_init(const WT& W, Env<NB>& e) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         int c = b < W.n_bodies ? W.collider_of[b] : 0;
@@ -37,10 +66,12 @@ __device__ __forceinline__ void env_init(const DevWorld& W, Env<NB>& e) {
     e.order = 0;
     e.count = 0;
     e.used = 0;
+    e.spair[0] = e.spair[1] = 0;
+    e.sns = 0;
 }
 
-template <int NB>
-__device__ __forceinline__ void env_load(const DevWorld& W, Env<NB>& e, const uint32_t* __restrict__ st, int64_t n, int64_t i) {
+template <int NB, class WT>
+__device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, const uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto ld = [&](int f) { return __uint_as_float(st[(int64_t)f * n + i]); };
     uint32_t fl = st[(int64_t)F_FLAGS * n + i];
     e.sleeping = fl & 0xffu;
@@ -64,6 +95,8 @@ __device__ __forceinline__ void env_load(const DevWorld& W, Env<NB>& e, const ui
     int base = F_DYN + 8 * (W.n_bodies - 1);
     e.order = 0xfedcba9876543210ull;
     e.used = (1u << e.count) - 1u;
+    e.spair[0] = e.spair[1] = 0;
+    e.sns = 0;
 #pragma unroll 1
     for (int k = 0; k < e.count; ++k) {
         int f = base + MF_WORDS * k;
@@ -73,8 +106,8 @@ __device__ __forceinline__ void env_load(const DevWorld& W, Env<NB>& e, const ui
     }
 }
 
-template <int NB>
-__device__ __forceinline__ void env_store(const DevWorld& W, const Env<NB>& e, uint32_t* __restrict__ st, int64_t n, int64_t i) {
+template <int NB, class WT>
+__device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto sf = [&](int f, float v) { st[(int64_t)f * n + i] = __float_as_uint(v); };
     int count = e.count < W.n_slots ? e.count : W.n_slots;
     st[(int64_t)F_FLAGS * n + i] = (e.sleeping & 0xffu) | e.flags | ((uint32_t)count << 16);
@@ -122,28 +155,49 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const DevWorld* __restric
 // Environment::step for every environment. moves != nullptr: one Move byte per environment and
 // n_steps == 1; else `uniform_move` for all, n_steps times. Also maintains the running minimum of
 // distance_to_goals, the step of the first win and the step counter.
-template <int NB>
-__global__ void __launch_bounds__(kBlock) step_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+template <int NB, class WT>
+__global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                       const uint8_t* __restrict__ moves, uint32_t uniform_move, int n_steps) {
-    __shared__ DevWorld W;
+    using Sim = Stepper<NB, MAXC, WT>;
+    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Sim::kRowQuads);
+    static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
+    __shared__ WT W;
+    __shared__ f4 row_pool[(kBlock / 32) * Sim::kRowQuads * kPoolRows];
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    // the row pool is handed out with warp shuffles, so every lane stays alive: lanes past the
+    // end replay the last environment and skip the stores
+    const bool live = i < n;
+    if (!live) i = n - 1;
     Env<NB> e;
     env_load(W, e, st, n, i);
     float score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
     int win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
     int steps = (int)st[(int64_t)F_STEPS * n + i];
     uint32_t mv = moves ? (moves[i] & 7u) : (uniform_move & 7u);
-    Stepper<NB, MAXC> sim(W, e);
+    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows, kPoolRows);
     sim.refresh_solver_contacts();
 #pragma unroll 1
-    for (int t = 0; t < n_steps; ++t) {
-        float d = sim.step(mv);
-        ++steps;
-        score = fminf(score, d);
-        if ((e.flags & FLAG_WON) && win_step < 0) win_step = steps;
+    for (int t = 0;; ++t) {
+        sim.detect_pending();
+        if (t == n_steps) break;
+        const int need = sim.begin_step(mv);
+        bool pending = true;
+#pragma unroll 1
+        while (true) {  // rounds: normally one -- every lane's rows fit the warp's pool
+            int total;
+            int base = warp_exclusive_sum(pending ? need : 0, total);
+            if (pending && base + need <= kPoolRows) {
+                float d = sim.finish_step(base);
+                ++steps;
+                score = fminf(score, d);
+                if ((e.flags & FLAG_WON) && win_step < 0) win_step = steps;
+                pending = false;
+            }
+            if (total <= kPoolRows) break;
+        }
     }
+    if (!live) return;
     env_store(W, e, st, n, i);
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
     st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
@@ -154,46 +208,65 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const DevWorld* __restrict
 // repeat_move times per gene, then number_of_steps % repeat_move default moves; score = min
 // distance_to_goals. early_exit reproduces the reference's break-on-win (including the tail's
 // extra step after a win); without it every step is executed (throughput runs).
-template <int NB>
-__global__ void __launch_bounds__(kBlock) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+template <int NB, class WT>
+__global__ void __launch_bounds__(kBlock, 7) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                          const uint8_t* __restrict__ genomes, int genome_len, int repeat_move,
                                                          int number_of_steps, int early_exit,
                                                          float* __restrict__ out_score, int32_t* __restrict__ out_win) {
-    __shared__ DevWorld W;
+    using Sim = Stepper<NB, MAXC, WT>;
+    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Sim::kRowQuads);
+    static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
+    __shared__ WT W;
+    __shared__ f4 row_pool[(kBlock / 32) * Sim::kRowQuads * kPoolRows];
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const bool live = i < n;  // see step_kernel
+    if (!live) i = n - 1;
     Env<NB> e;
     env_init(W, e);
-    Stepper<NB, MAXC> sim(W, e);
+    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows, kPoolRows);
     float score = __int_as_float(0x7f800000);
     int win_step = -1, steps = 0;
     const uint8_t* genome = genomes + i * (int64_t)genome_len;
     // one flat loop over the gene phase (genome_len x repeat_move steps) and the tail phase
     // (number_of_steps % repeat_move default moves): a win in the gene phase skips to the tail,
-    // which then runs one more step before it sees won() -- the reference's two loops
+    // which then runs one more step before it sees won() -- the reference's two loops. A lane
+    // whose rollout has ended idles in the loop until the whole warp is done, because the warp
+    // hands out the solver's row pool collectively every step.
     const int main_steps = genome_len * repeat_move;
     const int total = main_steps + number_of_steps % repeat_move;
-    int g = 0, rep = 0;
+    int g = 0, rep = 0, t = 0;
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
 #pragma unroll 1
-    for (int t = 0; t < total;) {
+    while (true) {
+        const bool run = t < total;
+        sim.detect_pending();
+        if (warp_all(!run)) break;
         const bool in_genes = t < main_steps;
-        float d = sim.step(in_genes ? gene : 0u);
-        ++steps;
-        ++t;
-        score = fminf(score, d);
-        bool won = (e.flags & FLAG_WON) != 0;
-        if (won && win_step < 0) win_step = steps;
-        if (in_genes && ++rep == repeat_move) {
-            rep = 0;
-            if (++g < genome_len) gene = genome[g] & 7u;
-        }
-        if (won && early_exit) {
-            if (!in_genes) break;
-            t = main_steps;
+        const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
+        bool pending = run;
+#pragma unroll 1
+        while (true) {  // rounds: normally one -- every lane's rows fit the warp's pool
+            int pool_total;
+            int base = warp_exclusive_sum(pending ? need : 0, pool_total);
+            if (pending && base + need <= kPoolRows) {
+                float d = sim.finish_step(base);
+                ++steps;
+                ++t;
+                score = fminf(score, d);
+                bool won = (e.flags & FLAG_WON) != 0;
+                if (won && win_step < 0) win_step = steps;
+                if (in_genes && ++rep == repeat_move) {
+                    rep = 0;
+                    if (++g < genome_len) gene = genome[g] & 7u;
+                }
+                if (won && early_exit) t = in_genes ? main_steps : total;
+                pending = false;
+            }
+            if (pool_total <= kPoolRows) break;
         }
     }
+    if (!live) return;
     env_store(W, e, st, n, i);
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
     st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;

@@ -19,7 +19,12 @@ constexpr int MAXG = PRL_MAX_GOALS;
 constexpr int MAXC = PRL_MAX_CONTACTS;       // manifold slots per environment
 constexpr int MF_WORDS = 15;                 // HBM words per manifold slot (see prl_device.cuh)
 
-struct alignas(16) DevWorld {
+// MC / MP / MG: collider, pair and goal capacity. The host always builds the full-size DevWorld;
+// kernels of small worlds stage a compact copy (DevWorldSmall) so that shared memory goes to the
+// solver's row pool instead of empty table slots.
+template <int MC, int MP, int MG>
+struct alignas(16) DevWorldT {
+    static constexpr int kMaxColliders = MC, kMaxPairs = MP, kMaxGoals = MG;
     int32_t n_colliders, n_bodies, n_pairs, n_goals;
     int32_t n_player_pairs;  // pairs whose collider1 is the player capsule come first
     int32_t n_slots;         // manifold slots kept per environment in HBM = min(n_pairs, MAXC)
@@ -29,20 +34,27 @@ struct alignas(16) DevWorld {
     float dt, inv_dt, erp_inv_dt, cfm_factor, prediction, allowed_linear_error, aabb_margin;
     float scale;  // BEVY_TO_PHYSICS_SCALE (distance_to_goals divides by it, common.rs:192)
     // colliders in insertion order; 0 = player capsule (common.rs:86, 125, 140-144)
-    float cx[MAXCOL], cy[MAXCOL], cc[MAXCOL], cs[MAXCOL];  // pose (initial pose for pushable blocks)
-    float hx[MAXCOL], hy[MAXCOL];                          // cuboid half extents
-    float amnx[MAXCOL], amny[MAXCOL], amxx[MAXCOL], amxy[MAXCOL];  // loosened AABB of fixed colliders
-    int8_t body_of[MAXCOL];                                // -1: parent-less (fixed) collider
+    float cx[MC], cy[MC], cc[MC], cs[MC];  // pose (initial pose for pushable blocks)
+    float hx[MC], hy[MC];                  // cuboid half extents
+    float amnx[MC], amny[MC], amxx[MC], amxy[MC];  // loosened AABB of fixed colliders
+    int8_t body_of[MC];                    // -1: parent-less (fixed) collider
     // bodies in handle order; 0 = player
     float inv_mass[MAXB], inv_inertia_sqrt[MAXB], ccd_thickness[MAXB];
-    float gdv_x[MAXB], gdv_y[MAXB];                        // 0 + (force * inv_mass) * dt with force = mass * gravity
+    float gdv_x[MAXB], gdv_y[MAXB];        // 0 + (force * inv_mass) * dt with force = mass * gravity
     int32_t collider_of[MAXB];
     // candidate pairs, ascending (collider1, collider2), fixed-fixed excluded
-    uint8_t pair_c1[MAXP], pair_c2[MAXP];
+    uint8_t pair_c1[MP], pair_c2[MP];
     // goals (common.rs:148-157, 175-195)
-    float gx[MAXG], gy[MAXG], ghw[MAXG], ghh[MAXG];        // centre, width/2, height/2
-    float gxax[MAXG], gxay[MAXG], gyax[MAXG], gyay[MAXG];  // Quat::from_rotation_z(rot) * X / Y, truncated
+    float gx[MG], gy[MG], ghw[MG], ghh[MG];        // centre, width/2, height/2
+    float gxax[MG], gxay[MG], gyax[MG], gyay[MG];  // Quat::from_rotation_z(rot) * X / Y, truncated
 };
+using DevWorld = DevWorldT<MAXCOL, MAXP, MAXG>;
+using DevWorldSmall = DevWorldT<16, 64, 4>;
+
+template <class WT>
+inline bool world_fits(const DevWorld& w) {
+    return w.n_colliders <= WT::kMaxColliders && w.n_pairs <= WT::kMaxPairs && w.n_goals <= WT::kMaxGoals;
+}
 
 // ---- HBM state layout of a batch: structure of arrays, one 32-bit word per field per environment:
 // word(f, env) = state[f * n_envs + env]. Fields:

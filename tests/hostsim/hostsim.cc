@@ -10,6 +10,9 @@
 
 using namespace prl;
 
+static int g_pool_rows = 64;
+extern "C" void hs_set_pool_rows(int rows) { g_pool_rows = rows < 32 ? 32 : (rows > 64 ? 64 : rows); }
+
 template <int NB>
 static void init_env(const DevWorld& W, Env<NB>& e) {
     memset(&e, 0, sizeof e);
@@ -25,7 +28,8 @@ static float rollout(const DevWorld& W, const uint8_t* genome, int genome_len, i
                      int early_exit, float* traj, int* win_out, int* steps_out, int* overflow) {
     static Env<NB> e;
     init_env(W, e);
-    Stepper<NB, MAXC> sim(W, e);
+    static f4 pool[4 * 64];
+    Stepper<NB, MAXC> sim(W, e, pool, g_pool_rows);
     float score = INFINITY;
     int win = -1, steps = 0;
     auto record = [&]() {
@@ -41,6 +45,7 @@ static float rollout(const DevWorld& W, const uint8_t* genome, int genome_len, i
         for (int r = 0; r < repeat_move; ++r) {
             float d = sim.step(genome[g] & 7u);
             ++steps;
+            if (traj) sim.detect_pending();  // what a kernel does before it stores the state
             record();
             score = fminf(score, d);
             bool won = (e.flags & FLAG_WON) != 0;
@@ -51,12 +56,14 @@ static float rollout(const DevWorld& W, const uint8_t* genome, int genome_len, i
     for (int r = 0; r < number_of_steps % repeat_move; ++r) {
         float d = sim.step(0u);
         ++steps;
+        if (traj) sim.detect_pending();
         record();
         score = fminf(score, d);
         bool won = (e.flags & FLAG_WON) != 0;
         if (won && win < 0) win = steps;
         if (won && early_exit) break;
     }
+    sim.detect_pending();
     *win_out = win;
     *steps_out = steps;
     *overflow = (e.flags & FLAG_OVERFLOW) ? 1 : 0;

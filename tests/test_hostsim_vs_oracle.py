@@ -60,6 +60,20 @@ def test_trajectories_bit_exact(name):
         assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
 
 
+def test_row_pool_size_does_not_change_results():
+    """The solver's constraint rows live in a shared-memory pool whose rows are XOR-swizzled;
+    the pool's size must not matter."""
+    world = world_dict("push")
+    hostsim().hs_set_pool_rows(32)
+    try:
+        for g in random_genomes(3, 50, 12):
+            t, _, _, _ = host_rollout(world, g, 20, 1000, False)
+            o = oracle_traj(world, g, 20, 1000)
+            assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
+    finally:
+        hostsim().hs_set_pool_rows(64)
+
+
 @pytest.mark.parametrize("name", WORLDS)
 def test_rollout_scores_and_early_exit(name):
     world = world_dict(name)
