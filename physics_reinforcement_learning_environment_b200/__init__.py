@@ -8,7 +8,10 @@ from . import _lib
 from ._lib import PrlError
 from .world import Move, ObjectAndTransform, World, WorldObject
 from .batched import BatchedEnvironment
+from .genetic import GaPopulation, GeneticAgent, GeneticAlgorithm
+from .parallel import gather_generation, slice_bounds
 
 _lib.lib()  # fail loudly at import time if the native library is absent
 
-__all__ = ["World", "WorldObject", "ObjectAndTransform", "Move", "BatchedEnvironment", "PrlError"]
+__all__ = ["World", "WorldObject", "ObjectAndTransform", "Move", "BatchedEnvironment", "GeneticAlgorithm", "GeneticAgent",
+           "GaPopulation", "gather_generation", "slice_bounds", "PrlError"]

@@ -154,6 +154,7 @@ int prl_batch_create(const prl_world* w, int64_t n_envs, int32_t device, void* s
     b->words = state_words(w->dev.n_bodies, w->dev.n_slots);
     cudaError_t e1 = cudaMalloc(&b->dev_world, sizeof(DevWorld));
     cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&b->state, (size_t)b->words * (size_t)n_envs * 4u) : e1;
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&b->overflow, sizeof(int));
     if (e2 != cudaSuccess) {
         set_error("cudaMalloc of %d state words x %lld environments failed: %s", b->words, (long long)n_envs, cudaGetErrorString(e2));
         if (b->dev_world) cudaFree(b->dev_world);
@@ -179,6 +180,7 @@ void prl_batch_destroy(prl_batch* b) {
     cudaStreamSynchronize(b->stream);
     if (b->dev_world) cudaFree(b->dev_world);
     if (b->state) cudaFree(b->state);
+    if (b->overflow) cudaFree(b->overflow);
     if (b->stage) cudaFree(b->stage);
     if (b->stage2) cudaFree(b->stage2);
     delete b;
@@ -192,6 +194,7 @@ int64_t prl_batch_state_bytes(const prl_batch* b) { return b ? (int64_t)b->words
 int prl_batch_reset(prl_batch* b) {
     if (!b) { set_error("prl_batch_reset: null batch"); return PRL_ERR_INVALID; }
     DeviceGuard g(b->device);
+    CUDA_TRY(cudaMemsetAsync(b->overflow, 0, sizeof(int), b->stream));
     reset_kernel<<<grid_for(b->n), kBlock, 0, b->stream>>>(b->dev_world, b->state, b->n);
     ++b->launches;
     CUDA_TRY(cudaGetLastError());
@@ -199,7 +202,7 @@ int prl_batch_reset(prl_batch* b) {
 }
 
 static int launch_step(prl_batch* b, const uint8_t* dev_moves, uint32_t uniform, int n_steps) {
-    PRL_DISPATCH(pick_variant(b->host_world), step_kernel, grid_for(b->n), b->stream, b->dev_world, b->state, b->n, dev_moves, uniform, n_steps);
+    PRL_DISPATCH(pick_variant(b->host_world), step_kernel, grid_for(b->n), b->stream, b->dev_world, b->state, b->n, dev_moves, uniform, n_steps, b->overflow);
     ++b->launches;
     CUDA_TRY(cudaGetLastError());
     return PRL_OK;
@@ -319,7 +322,7 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
     float* ds = score_host ? nullptr : out_score;
     int32_t* dw = win_host ? nullptr : out_step_of_win;
     PRL_DISPATCH(pick_variant(b->host_world), rollout_kernel, grid_for(b->n), b->stream, b->dev_world, b->state, b->n, dg, genome_len,
-                 repeat_move, number_of_steps, early_exit, ds, dw);
+                 repeat_move, number_of_steps, early_exit, ds, dw, b->overflow);
     ++b->launches;
     CUDA_TRY(cudaGetLastError());
     // host outputs come straight from the state arrays the kernel also fills
@@ -332,7 +335,13 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
 int prl_batch_sync(prl_batch* b) {
     if (!b) { set_error("prl_batch_sync: null batch"); return PRL_ERR_INVALID; }
     DeviceGuard g(b->device);
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, b->overflow, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
+    if (flag) {
+        set_error("an environment needed more than PRL_MAX_CONTACTS=%d simultaneous contact manifolds; its trajectory is no longer exact", PRL_MAX_CONTACTS);
+        return PRL_ERR_OVERFLOW;
+    }
     return PRL_OK;
 }
 

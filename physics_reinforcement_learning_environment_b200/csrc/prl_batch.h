@@ -19,6 +19,7 @@ struct prl_batch {
     prl::DevWorld host_world;
     prl::DevWorld* dev_world = nullptr;
     uint32_t* state = nullptr;     // SoA words, [state_words][n]
+    int* overflow = nullptr;       // device flag: some environment ran out of manifold slots
     int64_t n = 0;
     int words = 0;
     int device = 0;

@@ -4,7 +4,9 @@
 // `choose_multiple_weighted` (Efraimidis-Spirakis keys over the whole generation: O(N) per child,
 // O(N^2) per generation). Here one generation is:
 //   best      min (first index on ties, Iterator::min_by) and max of the global scores
-//   weights   w_i = max_score + 1 - score_i (main.rs:135), inclusive prefix sum in f64
+//   weights   w_i = max_score + 1 - score_i (main.rs:135) in f32, then fixed point (2^-20) so that
+//             their inclusive prefix sum is exact integer arithmetic: the same on any GPU count
+//             and in any reduction order
 //   breed     one thread per child: parent 1 by inverse-CDF binary search, parent 2 likewise with
 //             rejection of parent 1 (the same distribution as weighted sampling of 2 without
 //             replacement), uniform crossover per gene, per-bit mutation (main.rs:140-158),
@@ -39,8 +41,8 @@ struct prl_ga {
     float* local_scores = nullptr;      // n_local
     uint8_t* global_genomes = nullptr;  // n_global x genome_len (parents)
     float* global_scores = nullptr;     // n_global
-    double* cdf = nullptr;              // n_global inclusive prefix sums of the weights
-    double* block_sums = nullptr;
+    unsigned long long* cdf = nullptr;  // n_global inclusive prefix sums of the fixed-point weights
+    unsigned long long* block_sums = nullptr;
     unsigned long long* best_key = nullptr;  // [0] = score bits << 32 | index (min), [1] = max score bits
     unsigned long long* steps_sum = nullptr;
     int64_t generation = 0;
@@ -112,55 +114,60 @@ __global__ void best_kernel(const float* __restrict__ scores, int64_t n, unsigne
     }
 }
 
-// weights (main.rs:135) and their per-chunk sums
-__global__ void weight_block_sums_kernel(const float* __restrict__ scores, int64_t n, float max_score, double* __restrict__ block_sums) {
-    __shared__ double warp_sums[kGaBlock / 32];
+// main.rs:135: weight of an agent, as 44.20 fixed point (scores are pixel distances, far below 2^24)
+__device__ __forceinline__ unsigned long long fixed_weight(float max_score, float score) {
+    float w = max_score + 1.0f - score;
+    if (!(w > 0.0f)) return 0ull;  // +inf scores (no step taken) and NaN get no offspring
+    return (unsigned long long)llrint((double)w * 1048576.0);
+}
+// per-chunk sums of the weights
+__global__ void weight_block_sums_kernel(const float* __restrict__ scores, int64_t n, float max_score, unsigned long long* __restrict__ block_sums) {
+    __shared__ unsigned long long warp_sums[kGaBlock / 32];
     int64_t base = (int64_t)blockIdx.x * kScanChunk;
-    double s = 0.0;
+    unsigned long long s = 0;
     for (int j = threadIdx.x; j < kScanChunk; j += kGaBlock) {
         int64_t i = base + j;
-        if (i < n) s += (double)(max_score + 1.0f - scores[i]);
+        if (i < n) s += fixed_weight(max_score, scores[i]);
     }
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double t = 0.0;
+        unsigned long long t = 0;
         for (int w = 0; w < kGaBlock / 32; ++w) t += warp_sums[w];
         block_sums[blockIdx.x] = t;
     }
 }
 // exclusive scan of the chunk sums, in place, by one thread (<= N/1024 values)
-__global__ void scan_block_sums_kernel(double* __restrict__ block_sums, int64_t nblocks) {
+__global__ void scan_block_sums_kernel(unsigned long long* __restrict__ block_sums, int64_t nblocks) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        double run = 0.0;
-        for (int64_t b = 0; b < nblocks; ++b) { double v = block_sums[b]; block_sums[b] = run; run += v; }
+        unsigned long long run = 0;
+        for (int64_t b = 0; b < nblocks; ++b) { unsigned long long v = block_sums[b]; block_sums[b] = run; run += v; }
     }
 }
 // inclusive prefix sums inside each chunk + the chunk's offset
-__global__ void weight_scan_kernel(const float* __restrict__ scores, int64_t n, float max_score, const double* __restrict__ block_offsets,
-                                   double* __restrict__ cdf) {
-    __shared__ double warp_tot[kGaBlock / 32];
+__global__ void weight_scan_kernel(const float* __restrict__ scores, int64_t n, float max_score, const unsigned long long* __restrict__ block_offsets,
+                                   unsigned long long* __restrict__ cdf) {
+    __shared__ unsigned long long warp_tot[kGaBlock / 32];
     int64_t base = (int64_t)blockIdx.x * kScanChunk;
     constexpr int per = kScanChunk / kGaBlock;  // consecutive elements per thread
-    double v[per];
-    double run = 0.0;
+    unsigned long long v[per];
+    unsigned long long run = 0;
 #pragma unroll
     for (int j = 0; j < per; ++j) {
         int64_t i = base + (int64_t)threadIdx.x * per + j;
-        double w = i < n ? (double)(max_score + 1.0f - scores[i]) : 0.0;
-        run += w;
+        run += i < n ? fixed_weight(max_score, scores[i]) : 0ull;
         v[j] = run;
     }
-    double incl = run;
+    unsigned long long incl = run;
     int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int o = 1; o < 32; o <<= 1) {
-        double up = __shfl_up_sync(0xffffffffu, incl, o);
+        unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += up;
     }
     if (lane == 31) warp_tot[warp] = incl;
     __syncthreads();
-    double off = block_offsets[blockIdx.x];
+    unsigned long long off = block_offsets[blockIdx.x];
     for (int w = 0; w < warp; ++w) off += warp_tot[w];
     off += incl - run;
 #pragma unroll
@@ -170,11 +177,11 @@ __global__ void weight_scan_kernel(const float* __restrict__ scores, int64_t n, 
     }
 }
 
-__device__ __forceinline__ int64_t pick(const double* __restrict__ cdf, int64_t n, double total, uint32_t hi, uint32_t lo) {
-    // 53 random bits -> [0,1)
-    double u = (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
-    double target = u * total;
-    int64_t a = 0, b = n - 1;  // first index with cdf > target
+// weighted pick by inverse CDF: a 64-bit random word scaled to [0, total), then the first index
+// whose inclusive prefix sum exceeds it
+__device__ __forceinline__ int64_t pick(const unsigned long long* __restrict__ cdf, int64_t n, unsigned long long total, uint32_t hi, uint32_t lo) {
+    unsigned long long target = __umul64hi(((unsigned long long)hi << 32) | lo, total);
+    int64_t a = 0, b = n - 1;
     while (a < b) {
         int64_t m = (a + b) >> 1;
         if (cdf[m] > target) b = m; else a = m + 1;
@@ -183,7 +190,7 @@ __device__ __forceinline__ int64_t pick(const double* __restrict__ cdf, int64_t 
 }
 
 // main.rs:126-158 for the children [local_off, local_off + n_local)
-__global__ void breed_kernel(const uint8_t* __restrict__ parents, const double* __restrict__ cdf, int64_t n_global, int genome_len,
+__global__ void breed_kernel(const uint8_t* __restrict__ parents, const unsigned long long* __restrict__ cdf, int64_t n_global, int genome_len,
                              uint8_t* __restrict__ children, int64_t n_local, int64_t local_off, float mutation_rate, int keep_best,
                              int64_t best_index, uint64_t seed, uint32_t generation) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -195,7 +202,7 @@ __global__ void breed_kernel(const uint8_t* __restrict__ parents, const double* 
         for (int g = 0; g < genome_len; ++g) out[g] = src[g];
         return;
     }
-    double total = cdf[n_global - 1];
+    unsigned long long total = cdf[n_global - 1];
     uint32_t r[4];
     philox4x32(seed, (uint64_t)child, generation, kDrawParents, r);
     int64_t p1 = pick(cdf, n_global, total, r[0], r[1]);

@@ -157,7 +157,8 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const DevWorld* __restric
 // distance_to_goals, the step of the first win and the step counter.
 template <int NB, class WT>
 __global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
-                                                      const uint8_t* __restrict__ moves, uint32_t uniform_move, int n_steps) {
+                                                      const uint8_t* __restrict__ moves, uint32_t uniform_move, int n_steps,
+                                                      int* __restrict__ overflow) {
     using Sim = Stepper<NB, MAXC, WT>;
     constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Sim::kRowQuads);
     static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restr
         }
     }
     if (!live) return;
+    if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);  // more live manifolds than PRL_MAX_CONTACTS: reported by prl_batch_sync
     env_store(W, e, st, n, i);
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
     st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
@@ -212,7 +214,8 @@ template <int NB, class WT>
 __global__ void __launch_bounds__(kBlock, 7) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                          const uint8_t* __restrict__ genomes, int genome_len, int repeat_move,
                                                          int number_of_steps, int early_exit,
-                                                         float* __restrict__ out_score, int32_t* __restrict__ out_win) {
+                                                         float* __restrict__ out_score, int32_t* __restrict__ out_win,
+                                                         int* __restrict__ overflow) {
     using Sim = Stepper<NB, MAXC, WT>;
     constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Sim::kRowQuads);
     static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(kBlock, 7) rollout_kernel(const DevWorld* __re
         }
     }
     if (!live) return;
+    if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);  // more live manifolds than PRL_MAX_CONTACTS: reported by prl_batch_sync
     env_store(W, e, st, n, i);
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
     st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;

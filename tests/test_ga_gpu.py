@@ -1,0 +1,172 @@
+"""The genetic algorithm (reference src/main.rs:41-163) on the device, through the C ABI:
+bit-exact against tests/ga_ref.py (numpy restatement with the same Philox counters) and the
+oracle's rollouts, sharding invariance with emulated ranks, statistics of selection / crossover /
+mutation against the reference's semantics, and the train() protocol."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import ga_ref
+import physics_reinforcement_learning_environment_b200 as prl
+from conftest import world_dict, world_text
+from oracle import binding as oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def make(world_name="right", **kw):
+    cfg = dict(number_of_steps=200, number_of_agents=96, repeat_move=20, mutation_rate=0.1, keep_best=False, seed=1234)
+    cfg.update(kw)
+    return prl.GaPopulation(prl.World.from_json(world_text(world_name)), **cfg), cfg
+
+
+def test_init_matches_philox_reference_and_oracle_scores():
+    pop, cfg = make()
+    pop.init()
+    genomes = pop.local_genomes()
+    assert genomes.shape == (96, 10)  # number_of_steps / repeat_move genes (main.rs:75)
+    assert np.array_equal(genomes, ga_ref.init_genomes(96, 10, cfg["seed"]))
+    rs, _, _ = oracle.rollout_batch(world_dict("right"), genomes, 20, 200, early_exit=True, n_threads=os.cpu_count())
+    assert np.array_equal(bits(pop.local_scores()), bits(rs))
+    score, genome, idx = pop.best()
+    bi, bmin, _ = ga_ref.best(rs)
+    assert idx == bi and bits(score) == bits(bmin) and np.array_equal(genome, genomes[bi])
+
+
+@pytest.mark.parametrize("keep_best", [False, True])
+def test_next_generation_children_bit_exact(keep_best):
+    pop, cfg = make("push", keep_best=keep_best, number_of_agents=64, number_of_steps=300, mutation_rate=0.25)
+    pop.init()
+    for gen in (1, 2):
+        parents, scores = pop.local_genomes(), pop.local_scores()
+        pop.next_generation()
+        assert pop.generation == gen
+        ref, _ = ga_ref.breed(parents, scores, gen, cfg["seed"], cfg["mutation_rate"], keep_best)
+        children = pop.local_genomes()
+        for c in range(64):
+            assert np.array_equal(children[c], ref[c]), (gen, c)
+        rs, _, _ = oracle.rollout_batch(world_dict("push"), children, 20, 300, early_exit=True, n_threads=os.cpu_count())
+        assert np.array_equal(bits(pop.local_scores()), bits(rs))
+    if keep_best:
+        # the elite is carried over unchanged (main.rs:126-131) and its score is its old score
+        bi, bmin, _ = ga_ref.best(scores)
+        assert np.array_equal(children[0], parents[bi]) and bits(pop.local_scores()[0]) == bits(bmin)
+
+
+def test_population_sharding_does_not_change_the_result():
+    """Three emulated ranks on one GPU, exchanging slices by hand, against one rank."""
+    import torch
+    world = prl.World.from_json(world_text("jump"))
+    kw = dict(number_of_steps=240, number_of_agents=100, repeat_move=20, mutation_rate=0.1, keep_best=True, seed=77)
+    single = prl.GaPopulation(world, **kw)
+    single.init()
+    ranks = [prl.GaPopulation(world, rank=r, n_ranks=3, **kw) for r in range(3)]
+    for p in ranks:
+        p.init()
+
+    def exchange():
+        torch.cuda.synchronize()
+        for p in ranks:
+            _, _, gs, gg = p.tensors()
+            for q in ranks:
+                ls, lg, _, _ = q.tensors()
+                gs[q.local_offset:q.local_offset + q.local_count].copy_(ls)
+                gg[q.local_offset:q.local_offset + q.local_count].copy_(lg)
+        torch.cuda.synchronize()
+
+    for gen in range(3):
+        exchange()
+        s1 = single.best()
+        for p in ranks:
+            sr = p.best()
+            assert bits(sr[0]) == bits(s1[0]) and sr[2] == s1[2] and np.array_equal(sr[1], s1[1])
+        whole = np.concatenate([p.local_genomes() for p in ranks])
+        assert np.array_equal(whole, single.local_genomes())
+        assert np.array_equal(bits(np.concatenate([p.local_scores() for p in ranks])), bits(single.local_scores()))
+        single.next_generation()
+        for p in ranks:
+            p.next_generation()
+
+
+def test_selection_crossover_mutation_statistics():
+    """choose_multiple_weighted(2, w = max + 1 - score) (main.rs:134-138): two DISTINCT parents,
+    the first drawn with probability w_i / sum(w); uniform crossover (main.rs:140-147); each of
+    the three bits re-drawn with probability mutation_rate (main.rs:148-158), i.e. flipped with
+    probability rate / 2."""
+    n, L = 64, 10
+    pop, cfg = make("right", number_of_agents=n, mutation_rate=0.2, seed=9)
+    pop.init()
+    parents, scores = pop.local_genomes(), pop.local_scores()
+    w = np.array(ga_ref.fixed_weights(scores), dtype=np.float64)
+    p_first = w / w.sum()
+    counts = np.zeros(n)
+    pairs, flips, from_p1, total_genes = 0, 0, 0, 0
+    gens = 60
+    for gen in range(1, gens + 1):
+        _, chosen = ga_ref.breed(parents, scores, gen, cfg["seed"], 0.0, False)  # which parents the device must have used
+        no_mut, _ = ga_ref.breed(parents, scores, gen, cfg["seed"], 0.0, False)
+        mut, _ = ga_ref.breed(parents, scores, gen, cfg["seed"], 0.2, False)
+        for c in range(n):
+            p1, p2 = chosen[c]
+            assert p1 != p2
+            counts[p1] += 1
+            pairs += 1
+            x = no_mut[c] ^ mut[c]
+            flips += int(np.unpackbits(x.astype(np.uint8)).sum())
+            differ = parents[p1] != parents[p2]
+            from_p1 += int((no_mut[c][differ] == parents[p1][differ]).sum())
+            total_genes += int(differ.sum())
+    # the device agrees with the restatement on generation 1 (bit-exact test above covers more)
+    pop.next_generation()
+    ref1, _ = ga_ref.breed(parents, scores, 1, cfg["seed"], 0.2, False)
+    assert all(np.array_equal(pop.local_genomes()[c], ref1[c]) for c in range(n))
+    # first-parent frequencies follow the weights (chi-square, 63 dof: mean 63, sd 11)
+    expected = p_first * pairs
+    chi2 = float(((counts - expected) ** 2 / expected).sum())
+    assert chi2 < 63 + 5 * 11.2, chi2
+    # crossover is a fair coin on genes where the parents differ
+    assert abs(from_p1 / total_genes - 0.5) < 0.02
+    # each bit flips with probability rate / 2 = 0.1
+    assert abs(flips / (pairs * L * 3) - 0.1) < 0.01
+
+
+def test_train_protocol_and_learning_on_right_json():
+    """train() sends (best score, agent) once per generation until the receiver goes away
+    (main.rs:112-124); on right.json the population learns to walk right and wins."""
+    world = prl.World.from_json(world_text("right"))
+    algo = prl.GeneticAlgorithm(number_of_steps=400, number_of_agents=512, repeat_move=20, mutation_rate=0.1, keep_best=True, seed=5)
+    msgs = []
+
+    def sender(msg):
+        msgs.append(msg)
+        return len(msgs) < 12 and msg[0] > 0.0  # "receiver dropped" after a win or 12 generations
+
+    gens = algo.train(world, sender)
+    assert gens == len(msgs) and 1 <= gens <= 12
+    scores = [m[0] for m in msgs]
+    assert all(scores[i + 1] <= scores[i] for i in range(len(scores) - 1))  # keep_best: never worse
+    assert scores[-1] == 0.0
+    # replay the winning agent on the CPU environment, as the reference's visualiser does (train.rs:132-159)
+    agent = msgs[-1][1]
+    env = oracle.OracleEnv(world_dict("right"))
+    for _ in range(400):
+        env.step(agent.get_move(env).bits())
+        if env.won():
+            break
+    assert env.won()
+
+
+def test_ga_rejects_bad_configs():
+    world = prl.World.from_json(world_text("right"))
+    with pytest.raises(prl.PrlError):
+        prl.GaPopulation(world, number_of_agents=1)
+    with pytest.raises(prl.PrlError):
+        prl.GaPopulation(world, number_of_steps=10, repeat_move=20)
+    with pytest.raises(prl.PrlError):
+        prl.GaPopulation(prl.World.from_json('{"player_position":[0.0,0.0],"objects":[]}'))
