@@ -104,7 +104,7 @@ def run_reference(args, world_text, rank):
     oracle.lib()
     cores = os.cpu_count() or 1
     genome_len = args.horizon // args.repeat
-    sample_envs = max(cores * 8, 64)
+    sample_envs = max(cores * 256, 1024)  # ~1 s of host work per step
     for _ in range(args.warmup):
         cpu_reference_rate(world_text, sample_envs, genome_len, args.repeat, args.horizon, cores, 1)
     tot_steps, tot_time = 0, 0.0

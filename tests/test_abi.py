@@ -29,6 +29,13 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().prl_abi_version() == 1
 
 
+def test_rust_facade_binds_exactly_the_exported_symbols():
+    # rust/src/ffi.rs is the extern "C" block a maintainer adds to the reference crate
+    text = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    rust = sorted(set(re.findall(r"pub fn (prl_[a-z0-9_]+)\(", text)))
+    assert rust == declared_symbols()
+
+
 def test_product_does_not_link_or_import_the_oracle():
     # the oracle is test infrastructure: no product source may mention it
     pkg = os.path.join(ROOT, "physics_reinforcement_learning_environment_b200")

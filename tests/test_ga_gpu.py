@@ -170,3 +170,18 @@ def test_ga_rejects_bad_configs():
         prl.GaPopulation(world, number_of_steps=10, repeat_move=20)
     with pytest.raises(prl.PrlError):
         prl.GaPopulation(prl.World.from_json('{"player_position":[0.0,0.0],"objects":[]}'))
+
+
+def test_nccl_all_gather_on_real_gpus():
+    """Needs >= 2 visible GPUs (skipped on the 1-GPU box): tests/multi_gpu_ga_check.py under torchrun."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU visible")
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 4)}",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_ga_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "MULTI_GPU_GA_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
