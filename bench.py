@@ -133,7 +133,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--world", default="push")
+    ap.add_argument("--world", default="push", help="push | jump | right | synth64 (worlds/*.json)")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU")
     ap.add_argument("--horizon", type=int, default=2000, help="physics steps per rollout")
     ap.add_argument("--repeat", type=int, default=20)

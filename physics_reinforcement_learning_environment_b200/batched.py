@@ -82,13 +82,16 @@ class BatchedEnvironment:
         _lib.check(_lib.lib().prl_batch_won(self._h, _ptr(out, np.uint8, self.n_envs, "out")))
         return out
 
-    def state(self, env0: int = 0, n: Optional[int] = None) -> np.ndarray:
+    def state(self, env0: int = 0, n: Optional[int] = None, out=None):
         """Bodies of environments [env0, env0+n) as (n, n_bodies, 9) float32:
         x, y, cos, sin, vx, vy, angvel, sleep timer, sleeping -- the batched form of
-        rigid_body_set()/player_handle() (common.rs:201-211). Body 0 is the player."""
+        rigid_body_set()/player_handle() (common.rs:201-211), i.e. what `Agent::get_move(&self,
+        &Environment)` (algorithm.rs:9) can observe. Body 0 is the player. `out` may be a torch
+        CUDA tensor: the observation then stays on the device for a policy that runs there."""
         n = self.n_envs - env0 if n is None else n
-        out = np.empty((n, self.n_bodies, 9), dtype=np.float32)
-        _lib.check(_lib.lib().prl_batch_get_state(self._h, env0, n, out.ctypes.data))
+        if out is None:
+            out = np.empty((n, self.n_bodies, 9), dtype=np.float32)
+        _lib.check(_lib.lib().prl_batch_get_state(self._h, env0, n, _ptr(out, np.float32, n * self.n_bodies * 9, "out")))
         return out
 
     def rollout(self, genomes, repeat_move: int, number_of_steps: int, early_exit: bool = True,

@@ -179,3 +179,33 @@ def test_goalless_world_reports_no_goal():
     assert e.value.status == _lib.PRL_ERR_NO_GOAL
     with pytest.raises(prl.PrlError):
         env.rollout(np.zeros((4, 2), np.uint8), 1, 2)
+
+
+def test_closed_loop_policy_on_device_matches_cpu_agent():
+    """Agent::get_move(&mut self, &Environment) (algorithm.rs:9) in batch: observations stay on
+    the GPU (torch tensor), a policy computes the moves there, step() consumes them from device
+    memory. The same policy driven by the oracle's state must produce the same trajectories."""
+    import torch
+    name = "jump"
+    n, steps = 64, 400
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text(name)), n, stream=torch.cuda.current_stream().cuda_stream)
+    obs = torch.empty((n, env.n_bodies, 9), dtype=torch.float32, device="cuda")
+    thresholds = torch.linspace(0.0, 0.02, n, device="cuda")
+
+    def policy(o, thr):
+        # walk right; jump when horizontal speed has stalled below a per-agent threshold
+        vx = o[:, 0, 4]
+        return (2 + 4 * (vx < thr).to(torch.uint8)).to(torch.uint8)
+
+    oracles = [OracleEnv(world_dict(name)) for _ in range(n)]
+    for t in range(steps):
+        env.state(out=obs)
+        moves = policy(obs, thresholds).contiguous()
+        env.step(moves)
+        for i, o in enumerate(oracles):
+            vx = np.float32(o.state()[0][4])
+            o.step(6 if vx < np.float32(thresholds[i].item()) else 2)
+    torch.cuda.synchronize()
+    ref = np.stack([o.state() for o in oracles])
+    assert np.array_equal(bits(env.state()), bits(ref))
+    assert np.array_equal(env.won(), np.array([o.won() for o in oracles], np.uint8))
