@@ -23,6 +23,7 @@ struct prl_batch {
     int64_t n = 0;
     int words = 0;
     int device = 0;
+    int sm_count = 0;
     cudaStream_t stream = nullptr;
     // staging for host-side buffers
     void* stage = nullptr;

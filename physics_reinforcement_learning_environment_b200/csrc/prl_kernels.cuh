@@ -21,6 +21,16 @@ constexpr int kBlock = 64;
 // world (320 rows of 48 B), 12 KB beside the 6.1 KB full-size tables.
 template <class WT> struct PoolBytes { static constexpr int value = 12288; };
 template <> struct PoolBytes<DevWorldSmall> { static constexpr int value = 15360; };
+// Rollouts of large batches run ONE block of 448 threads per SM (the same 14 warps, 148 x 448 >=
+// 65536) with a block barrier at the top of every step: the step is ~4000 straight-line
+// instructions outside the solver's loops, and warps of one SM that are in the same phase of the
+// step share their instruction fetches (measured +19 % over 7 independent 64-thread blocks, whose
+// top stall was no_instruction). Small batches keep 64-thread blocks so they spread over the SMs.
+constexpr int kBigBlock = 448;
+template <class WT, int RQ>
+constexpr size_t rollout_smem_bytes(int block) {
+    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * PoolBytes<WT>::value;
+}
 
 // block-wide copy of the world tables into shared memory (compacting into WT's capacities)
 template <class WT>
@@ -210,8 +220,8 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restr
 // repeat_move times per gene, then number_of_steps % repeat_move default moves; score = min
 // distance_to_goals. early_exit reproduces the reference's break-on-win (including the tail's
 // extra step after a win); without it every step is executed (throughput runs).
-template <int NB, class WT>
-__global__ void __launch_bounds__(kBlock, 7) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+template <int NB, class WT, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : 7) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                          const uint8_t* __restrict__ genomes, int genome_len, int repeat_move,
                                                          int number_of_steps, int early_exit,
                                                          float* __restrict__ out_score, int32_t* __restrict__ out_win,
@@ -219,8 +229,9 @@ __global__ void __launch_bounds__(kBlock, 7) rollout_kernel(const DevWorld* __re
     using Sim = Stepper<NB, MAXC, WT>;
     constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Sim::kRowQuads);
     static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
-    __shared__ WT W;
-    __shared__ f4 row_pool[(kBlock / 32) * Sim::kRowQuads * kPoolRows];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WT& W = *reinterpret_cast<WT*>(smem_raw);
+    f4* row_pool = reinterpret_cast<f4*>(smem_raw + ((sizeof(WT) + 15) / 16) * 16);
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;  // see step_kernel
@@ -234,8 +245,9 @@ __global__ void __launch_bounds__(kBlock, 7) rollout_kernel(const DevWorld* __re
     // one flat loop over the gene phase (genome_len x repeat_move steps) and the tail phase
     // (number_of_steps % repeat_move default moves): a win in the gene phase skips to the tail,
     // which then runs one more step before it sees won() -- the reference's two loops. A lane
-    // whose rollout has ended idles in the loop until the whole warp is done, because the warp
-    // hands out the solver's row pool collectively every step.
+    // whose rollout has ended idles in the loop until the whole block is done: the warp hands
+    // out the solver's row pool collectively every step, and the block barrier at the top of the
+    // step keeps the SM's warps in the same phase of the step (shared instruction fetches).
     const int main_steps = genome_len * repeat_move;
     const int total = main_steps + number_of_steps % repeat_move;
     int g = 0, rep = 0, t = 0;
@@ -244,7 +256,7 @@ __global__ void __launch_bounds__(kBlock, 7) rollout_kernel(const DevWorld* __re
     while (true) {
         const bool run = t < total;
         sim.detect_pending();
-        if (warp_all(!run)) break;
+        if (__syncthreads_and(!run)) break;
         const bool in_genes = t < main_steps;
         const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
         bool pending = run;
