@@ -27,9 +27,17 @@ template <> struct PoolBytes<DevWorldSmall> { static constexpr int value = 15360
 // step share their instruction fetches (measured +19 % over 7 independent 64-thread blocks, whose
 // top stall was no_instruction). Small batches keep 64-thread blocks so they spread over the SMs.
 constexpr int kBigBlock = 448;
+// Every kRegroupEvery steps a 448-thread block re-deals its environments to its threads, sorted
+// by how many solver rows they needed last step (finished rollouts last): environments parked in
+// the HBM state arrays, a counting sort in shared memory, and each thread picks up its new
+// environment. Warps then hold environments of similar cost, so fewer lanes idle while their
+// neighbours solve contacts (and warps of finished rollouts only hit the barrier).
+constexpr int kRegroupEvery = 64;
+constexpr int kRegroupKeys = 34;  // 0 = finished, 1 + min(rows, 32)
+constexpr size_t kRegroupBytes = (kRegroupKeys + 2 * kBigBlock) * sizeof(int);
 template <class WT, int RQ>
 constexpr size_t rollout_smem_bytes(int block) {
-    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * PoolBytes<WT>::value;
+    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * PoolBytes<WT>::value + (block == kBigBlock ? kRegroupBytes : 0);
 }
 
 // block-wide copy of the world tables into shared memory (compacting into WT's capacities)
@@ -234,7 +242,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : 7) rollout_ker
     f4* row_pool = reinterpret_cast<f4*>(smem_raw + ((sizeof(WT) + 15) / 16) * 16);
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < n;  // see step_kernel
+    bool live = i < n;  // see step_kernel
     if (!live) i = n - 1;
     Env<NB> e;
     env_init(W, e);
@@ -250,13 +258,51 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : 7) rollout_ker
     // step keeps the SM's warps in the same phase of the step (shared instruction fetches).
     const int main_steps = genome_len * repeat_move;
     const int total = main_steps + number_of_steps % repeat_move;
-    int g = 0, rep = 0, t = 0;
+    int g = 0, rep = 0, t = 0, iter = 0;
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
+    int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kRowQuads * kPoolRows);  // only if BLOCK == kBigBlock
 #pragma unroll 1
     while (true) {
-        const bool run = t < total;
         sim.detect_pending();
-        if (__syncthreads_and(!run)) break;
+        if (__syncthreads_and(!(t < total))) break;
+        if (BLOCK == kBigBlock && iter > 0 && iter % kRegroupEvery == 0) {
+            // ---- regroup: park, sort, pick up (all threads of the block are here, nothing pending)
+            int* hist = regroup;
+            int* perm_env = regroup + kRegroupKeys;
+            int* perm_live = perm_env + kBigBlock;
+            if (live) {
+                env_store(W, e, st, n, i);
+                st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
+                st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
+                st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
+                st[(int64_t)F_ROLL * n + i] = (uint32_t)t;
+            }
+            const int key = t < total ? 1 + (sim.need < 32 ? sim.need : 32) : 0;
+            if (threadIdx.x < kRegroupKeys) hist[threadIdx.x] = 0;
+            __syncthreads();
+            const int pos = atomicAdd(&hist[key], 1);
+            __syncthreads();
+            int off = 0;
+            for (int k = key + 1; k < kRegroupKeys; ++k) off += hist[k];
+            perm_env[off + pos] = (int)(i - (int64_t)blockIdx.x * BLOCK);
+            perm_live[off + pos] = live ? 1 : 0;
+            __syncthreads();
+            i = (int64_t)blockIdx.x * BLOCK + perm_env[threadIdx.x];
+            live = perm_live[threadIdx.x] != 0;
+            env_load(W, e, st, n, i);
+            score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
+            win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
+            steps = (int)st[(int64_t)F_STEPS * n + i];
+            t = (int)st[(int64_t)F_ROLL * n + i];
+            sim.refresh_solver_contacts();
+            genome = genomes + i * (int64_t)genome_len;
+            g = t < main_steps ? t / repeat_move : genome_len;
+            rep = t < main_steps ? t % repeat_move : 0;
+            gene = g < genome_len ? (genome[g] & 7u) : 0u;
+            __syncthreads();  // hist / perm are reused by the next regroup
+        }
+        ++iter;
+        const bool run = t < total;
         const bool in_genes = t < main_steps;
         const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
         bool pending = run;

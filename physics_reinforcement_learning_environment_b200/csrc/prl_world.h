@@ -63,11 +63,14 @@ inline bool world_fits(const DevWorld& w) {
 //                                    bits 16-23 number of live manifold slots
 //   F_SCORE, F_WIN_STEP, F_STEPS     running min of distance_to_goals, 1-based step of the first
 //                                    won() (-1: none), steps since reset
+//   F_ROLL                           position of a rollout in its move schedule (only meaningful
+//                                    inside rollout_kernel, which parks environments here when it
+//                                    regroups them between threads)
 //   F_PLAYER .. +4                   x, y, vx, vy, sleep timer (rotations locked: cos=1, sin=0, w=0)
 //   F_DYN + 8*(b-1) .. +7            x, y, cos, sin, vx, vy, angvel, sleep timer of pushable block b
 //   slots                            n_slots x MF_WORDS: word 0 = pair | npts << 8, then local_n1,
 //                                    local_n2, 2 x (local_p1, local_p2, dist)
-enum { F_FLAGS = 0, F_SCORE = 1, F_WIN_STEP = 2, F_STEPS = 3, F_PLAYER = 4, F_DYN = 9 };
+enum { F_FLAGS = 0, F_SCORE = 1, F_WIN_STEP = 2, F_STEPS = 3, F_ROLL = 4, F_PLAYER = 5, F_DYN = 10 };
 constexpr uint32_t FLAG_WON = 1u << 8, FLAG_FRESH = 1u << 9, FLAG_OVERFLOW = 1u << 10;
 
 inline int state_slot_base(int n_bodies) { return F_DYN + 8 * (n_bodies - 1); }
