@@ -439,7 +439,7 @@ struct Env {
     f4 sc[S][2];
 };
 
-template <int NB, int S, class WT = DevWorld>
+template <int NB, int S, class WT = DevWorld, int POOL_ROWS = 64>
 struct Stepper {
     using E = Env<NB, S>;
     static constexpr int kGround = NB;  // pseudo body index of the fixed world: zero velocity, zero inverse mass
@@ -461,7 +461,7 @@ struct Stepper {
     const WT& W;
     E& e;
     f4* pool;
-    int pool_rows;
+    static constexpr int pool_rows = POOL_ROWS;  // rows in the warp's pool (plane stride, in quads)
     int rbase;          // first pool row of this lane, this step
     float tb_g1[2], tb_tg1[2];
     // constraint selection of the current step (begin_step -> finish_step)
@@ -471,8 +471,8 @@ struct Stepper {
     // collision detection owed for the poses of the last position update (detect_pending)
     uint32_t pend_moved;
     bool pend_all, first_step;
-    PRL_D Stepper(const WT& w, E& env, f4* warp_pool, int warp_pool_rows)
-        : W(w), e(env), pool(warp_pool), pool_rows(warp_pool_rows), rbase(0), active(0), cons(0), ncons(0), need(0), ntb(0), pend_moved(0),
+    PRL_D Stepper(const WT& w, E& env, f4* warp_pool)
+        : W(w), e(env), pool(warp_pool), rbase(0), active(0), cons(0), ncons(0), need(0), ntb(0), pend_moved(0),
           pend_all((env.flags & FLAG_FRESH) != 0), first_step(false) {
         tb_g1[0] = tb_g1[1] = tb_tg1[0] = tb_tg1[1] = 0.0f;
     }

@@ -177,8 +177,8 @@ template <int NB, class WT>
 __global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                       const uint8_t* __restrict__ moves, uint32_t uniform_move, int n_steps,
                                                       int* __restrict__ overflow) {
-    using Sim = Stepper<NB, MAXC, WT>;
-    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Sim::kRowQuads);
+    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Stepper<NB, MAXC, WT>::kRowQuads);
+    using Sim = Stepper<NB, MAXC, WT, kPoolRows>;
     static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
     __shared__ WT W;
     __shared__ f4 row_pool[(kBlock / 32) * Sim::kRowQuads * kPoolRows];
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restr
     int win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
     int steps = (int)st[(int64_t)F_STEPS * n + i];
     uint32_t mv = moves ? (moves[i] & 7u) : (uniform_move & 7u);
-    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows, kPoolRows);
+    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows);
     sim.refresh_solver_contacts();
 #pragma unroll 1
     for (int t = 0;; ++t) {
@@ -234,8 +234,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : 7) rollout_ker
                                                          int number_of_steps, int early_exit,
                                                          float* __restrict__ out_score, int32_t* __restrict__ out_win,
                                                          int* __restrict__ overflow) {
-    using Sim = Stepper<NB, MAXC, WT>;
-    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Sim::kRowQuads);
+    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Stepper<NB, MAXC, WT>::kRowQuads);
+    using Sim = Stepper<NB, MAXC, WT, kPoolRows>;
     static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WT& W = *reinterpret_cast<WT*>(smem_raw);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : 7) rollout_ker
     if (!live) i = n - 1;
     Env<NB> e;
     env_init(W, e);
-    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows, kPoolRows);
+    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows);
     float score = __int_as_float(0x7f800000);
     int win_step = -1, steps = 0;
     const uint8_t* genome = genomes + i * (int64_t)genome_len;

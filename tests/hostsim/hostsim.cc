@@ -23,13 +23,13 @@ static void init_env(const DevWorld& W, Env<NB>& e) {
     e.flags = FLAG_FRESH;
 }
 
-template <int NB>
+template <int NB, int PR>
 static float rollout(const DevWorld& W, const uint8_t* genome, int genome_len, int repeat_move, int number_of_steps,
                      int early_exit, float* traj, int* win_out, int* steps_out, int* overflow) {
     static Env<NB> e;
     init_env(W, e);
     static f4 pool[4 * 64];
-    Stepper<NB, MAXC> sim(W, e, pool, g_pool_rows);
+    Stepper<NB, MAXC, DevWorld, PR> sim(W, e, pool);
     float score = INFINITY;
     int win = -1, steps = 0;
     auto record = [&]() {
@@ -78,8 +78,11 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
     if (rc == PRL_OK) rc = build_dev_world(&w);
     if (rc != PRL_OK) return rc;
     const DevWorld& W = w.dev;
-    if (W.n_bodies == 1) *score = rollout<1>(W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow);
-    else if (W.n_bodies == 2) *score = rollout<2>(W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow);
-    else *score = rollout<MAXB>(W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow);
+#define HS_ARGS W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow
+    const bool small_pool = g_pool_rows < 64;
+    if (W.n_bodies == 1) *score = small_pool ? rollout<1, 32>(HS_ARGS) : rollout<1, 64>(HS_ARGS);
+    else if (W.n_bodies == 2) *score = small_pool ? rollout<2, 32>(HS_ARGS) : rollout<2, 64>(HS_ARGS);
+    else *score = small_pool ? rollout<MAXB, 32>(HS_ARGS) : rollout<MAXB, 64>(HS_ARGS);
+#undef HS_ARGS
     return 0;
 }
