@@ -63,3 +63,30 @@ def has_cuda():
         return _lib.lib().prl_device_count() > 0
     except Exception:
         return False
+
+
+def random_world(seed):
+    """A random level in the editor's schema: a long floor, fixed blocks (some rotated, some with
+    negative scales), 0-3 pushable blocks resting or dropped on the floor, 1-2 goals."""
+    rng = np.random.Generator(np.random.Philox(1000 + seed))
+    objs = [{"object": {"Block": {"fixed": True}}, "position": [300.0, -60.0, 1.0], "scale": [1600.0, 50.0],
+             "rotation": float(rng.uniform(-0.03, 0.03))}]
+    z = 2.0
+    for _ in range(int(rng.integers(1, 6))):
+        objs.append({"object": {"Block": {"fixed": True}},
+                     "position": [float(rng.uniform(-350, 900)), float(rng.uniform(-40, 30)), z],
+                     "scale": [float(rng.uniform(20, 120)) * (1 if rng.random() < 0.8 else -1), float(rng.uniform(15, 70))],
+                     "rotation": float(rng.uniform(-0.5, 0.5)) if rng.random() < 0.5 else 0.0})
+        z += 1.0
+    for _ in range(int(rng.integers(0, 4))):
+        objs.append({"object": {"Block": {"fixed": False}},
+                     "position": [float(rng.uniform(-250, 600)), float(rng.uniform(-20, 120)), z],
+                     "scale": [float(rng.uniform(25, 150)), float(rng.uniform(12, 60))],
+                     "rotation": float(rng.uniform(-0.4, 0.4)) if rng.random() < 0.5 else 0.0})
+        z += 1.0
+    for _ in range(int(rng.integers(1, 3))):
+        objs.append({"object": "Goal", "position": [float(rng.uniform(-400, 900)), float(rng.uniform(-30, 80)), z],
+                     "scale": [float(rng.uniform(30, 120)), float(rng.uniform(30, 120))], "rotation": float(rng.uniform(-0.6, 0.6))})
+        z += 1.0
+    order = rng.permutation(len(objs))  # object order decides collider / body indices
+    return {"player_position": [float(rng.uniform(-100, 100)), float(rng.uniform(20, 90))], "objects": [objs[i] for i in order]}

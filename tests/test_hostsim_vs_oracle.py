@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ROOT, WORLDS, n_bodies_of, random_genomes, synth_world, world_dict
+from conftest import ROOT, WORLDS, n_bodies_of, random_genomes, random_world, synth_world, world_dict
 from oracle.binding import OracleEnv
 
 _hs = None
@@ -108,3 +108,15 @@ def test_editor_edge_cases_rotations_negative_scales_two_pushables():
         o = oracle_traj(world, g, 15, 600)
         assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
         assert not np.isnan(t).any()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_worlds_bit_exact(seed):
+    """Randomly generated levels (rotated / mirrored fixed blocks, up to 3 pushable blocks in random
+    object order, several goals): every body, every step."""
+    world = random_world(seed)
+    for g in random_genomes(2, 30, 100 + seed):
+        t, _, _, _ = host_rollout(world, g, 20, 600, False)
+        o = oracle_traj(world, g, 20, 600)
+        assert not np.isnan(o).any()
+        assert np.array_equal(t.view(np.uint32), o.view(np.uint32))

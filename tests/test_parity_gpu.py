@@ -10,7 +10,7 @@ import pytest
 
 import physics_reinforcement_learning_environment_b200 as prl
 from physics_reinforcement_learning_environment_b200 import _lib
-from conftest import WORLDS, random_genomes, synth_world, world_dict, world_text
+from conftest import WORLDS, random_genomes, random_world, synth_world, world_dict, world_text
 from oracle import binding as oracle
 from oracle.binding import OracleEnv
 
@@ -209,3 +209,21 @@ def test_closed_loop_policy_on_device_matches_cpu_agent():
     ref = np.stack([o.state() for o in oracles])
     assert np.array_equal(bits(env.state()), bits(ref))
     assert np.array_equal(env.won(), np.array([o.won() for o in oracles], np.uint8))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_worlds_match_oracle(seed):
+    world = random_world(seed)
+    n, L, repeat, steps = 96, 30, 20, 600
+    genomes = random_genomes(n, L, 300 + seed)
+    env = prl.BatchedEnvironment(prl.World.from_json(json.dumps(world)), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    env.sync()
+    rs, rw, _ = oracle.rollout_batch(world, genomes, repeat, steps, False, n_threads=os.cpu_count())
+    assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
+    st = env.state(0, 3)
+    for i in range(3):
+        o = OracleEnv(world)
+        for t in range(steps):
+            o.step(int(genomes[i][t // repeat]))
+        assert np.array_equal(bits(st[i]), bits(o.state()))
