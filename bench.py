@@ -24,10 +24,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-B_ALG = {1: 56, 2: 120}  # algorithmic HBM bytes per env-step: 2 x (28 + 32 * n_pushable)
-
-
 def algorithmic_bytes(n_bodies):
+    """algorithmic HBM bytes per env-step: cross-step body state read once + written once"""
     return 2 * (28 + 32 * (n_bodies - 1))
 
 
