@@ -705,7 +705,8 @@ struct Stepper {
         for (int b = 0; b < NB; ++b) {
             if ((fell_asleep >> b) & 1u) {  // RigidBody::sleep
                 e.timer[b] = kTimeUntilSleep;
-                e.vx[b] = 0.0f; e.vy[b] = 0.0f; e.w[b] = 0.0f;
+                e.vx[b] = 0.0f; e.vy[b] = 0.0f;
+                if (b > 0) e.w[b] = 0.0f;  // the player's rotation is locked: (cos, sin, w) stay (1, 0, 0)
             }
         }
     }
@@ -966,8 +967,11 @@ struct Stepper {
                 float dangvel = W.inv_inertia_sqrt[b] * da[b];
                 e.vx[b] = e.vx[b] + dlx[b];
                 e.vy[b] = e.vy[b] + dly[b];
-                e.w[b] += dangvel;
-                e.x[b] = nx[b]; e.y[b] = ny[b]; e.c[b] = nc[b]; e.s[b] = ns[b];
+                e.x[b] = nx[b]; e.y[b] = ny[b];
+                // the player's rotation is locked (inverse inertia 0): its angular increment is an
+                // exact zero and (cos, sin, w) stay the constants (1, 0, 0), so they are never
+                // written and cost no registers
+                if (b > 0) { e.w[b] += dangvel; e.c[b] = nc[b]; e.s[b] = ns[b]; }
             }
         }
         return active;

@@ -76,7 +76,9 @@ __device__ __forceinline__ void env_init(const WT& W, Env<NB>& e) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         int c = b < W.n_bodies ? W.collider_of[b] : 0;
-        e.x[b] = W.cx[c]; e.y[b] = W.cy[c]; e.c[b] = W.cc[c]; e.s[b] = W.cs[c];
+        e.x[b] = W.cx[c]; e.y[b] = W.cy[c];
+        e.c[b] = b == 0 ? 1.0f : W.cc[c];  // the player is never rotated (common.rs:74-79)
+        e.s[b] = b == 0 ? 0.0f : W.cs[c];
         e.vx[b] = 0.0f; e.vy[b] = 0.0f; e.w[b] = 0.0f; e.timer[b] = 0.0f;
     }
     e.sleeping = 0;
