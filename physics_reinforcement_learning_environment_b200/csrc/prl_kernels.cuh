@@ -110,26 +110,35 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, const uint32_t
             e.c[b] = 1.0f;
         }
     }
-    // live manifolds are stored compacted in pair order: slot k = k-th manifold. The 15 HBM
-    // words of a slot are the first 15 words of the 16-word thread-local record.
+    // live manifolds are stored compacted in pair order: HBM slot k = k-th manifold. The 15 HBM
+    // words of a slot are the first 15 words of the 16-word thread-local record. Small worlds
+    // keep the manifold of pair p in record p (Stepper::kDirect), larger ones in record k.
+    constexpr bool direct = Stepper<NB, MAXC, WT>::kDirect;
     int base = F_DYN + 8 * (W.n_bodies - 1);
+    const int count = e.count;
     e.order = 0xfedcba9876543210ull;
-    e.used = (1u << e.count) - 1u;
+    e.used = direct ? 0u : (1u << count) - 1u;
     e.spair[0] = e.spair[1] = 0;
     e.sns = 0;
 #pragma unroll 1
-    for (int k = 0; k < e.count; ++k) {
+    for (int k = 0; k < count; ++k) {
         int f = base + MF_WORDS * k;
-        float* rec = &e.mf[k][0].x;
+        uint32_t h = st[(int64_t)f * n + i];
+        int slot = direct ? (int)(h & 0xffu) : k;
+        if (direct) e.used |= 1u << slot;
+        float* rec = &e.mf[slot][0].x;
+        rec[0] = __uint_as_float(h);
 #pragma unroll 1
-        for (int j = 0; j < MF_WORDS; ++j) rec[j] = ld(f + j);
+        for (int j = 1; j < MF_WORDS; ++j) rec[j] = ld(f + j);
     }
 }
 
 template <int NB, class WT>
 __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto sf = [&](int f, float v) { st[(int64_t)f * n + i] = __float_as_uint(v); };
-    int count = e.count < W.n_slots ? e.count : W.n_slots;
+    constexpr bool direct = Stepper<NB, MAXC, WT>::kDirect;
+    int count = direct ? __popc(e.used) : e.count;
+    count = count < W.n_slots ? count : W.n_slots;
     st[(int64_t)F_FLAGS * n + i] = (e.sleeping & 0xffu) | e.flags | ((uint32_t)count << 16);
     sf(F_PLAYER, e.x[0]); sf(F_PLAYER + 1, e.y[0]); sf(F_PLAYER + 2, e.vx[0]); sf(F_PLAYER + 3, e.vy[0]);
     sf(F_PLAYER + 4, e.timer[0]);
@@ -143,8 +152,10 @@ __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, uint32_
     }
     int base = F_DYN + 8 * (W.n_bodies - 1);
 #pragma unroll 1
+    uint32_t left = e.used;
     for (int k = 0; k < count; ++k) {
-        int slot = (int)((e.order >> (4 * k)) & 15u);
+        int slot = direct ? __ffs((int)left) - 1 : (int)((e.order >> (4 * k)) & 15u);
+        left &= left - 1;
         int f = base + MF_WORDS * k;
         const float* rec = &e.mf[slot][0].x;
         st[(int64_t)f * n + i] = __float_as_uint(rec[0]) & 0xfffu;  // pair | npts << 8 (solver-contact count is derived)

@@ -49,7 +49,7 @@ struct alignas(16) DevWorldT {
     float gxax[MG], gxay[MG], gyax[MG], gyay[MG];  // Quat::from_rotation_z(rot) * X / Y, truncated
 };
 using DevWorld = DevWorldT<MAXCOL, MAXP, MAXG>;
-using DevWorldSmall = DevWorldT<16, 64, 4>;
+using DevWorldSmall = DevWorldT<16, MAXC, 4>;  // <= MAXC pairs: manifold slot == pair index (Stepper::kDirect)
 
 template <class WT>
 inline bool world_fits(const DevWorld& w) {

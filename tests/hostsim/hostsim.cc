@@ -13,8 +13,8 @@ using namespace prl;
 static int g_pool_rows = 64;
 extern "C" void hs_set_pool_rows(int rows) { g_pool_rows = rows < 32 ? 32 : (rows > 64 ? 64 : rows); }
 
-template <int NB>
-static void init_env(const DevWorld& W, Env<NB>& e) {
+template <int NB, class WT>
+static void init_env(const WT& W, Env<NB>& e) {
     memset(&e, 0, sizeof e);
     for (int b = 0; b < NB; ++b) {
         int c = b < W.n_bodies ? W.collider_of[b] : 0;
@@ -23,13 +23,13 @@ static void init_env(const DevWorld& W, Env<NB>& e) {
     e.flags = FLAG_FRESH;
 }
 
-template <int NB, int PR>
-static float rollout(const DevWorld& W, const uint8_t* genome, int genome_len, int repeat_move, int number_of_steps,
+template <int NB, int PR, class WT>
+static float rollout(const WT& W, const uint8_t* genome, int genome_len, int repeat_move, int number_of_steps,
                      int early_exit, float* traj, int* win_out, int* steps_out, int* overflow) {
     static Env<NB> e;
     init_env(W, e);
     static f4 pool[4 * 64];
-    Stepper<NB, MAXC, DevWorld, PR> sim(W, e, pool);
+    Stepper<NB, MAXC, WT, PR> sim(W, e, pool);
     float score = INFINITY;
     int win = -1, steps = 0;
     auto record = [&]() {
@@ -70,6 +70,30 @@ static float rollout(const DevWorld& W, const uint8_t* genome, int genome_len, i
     return score;
 }
 
+// host copy of the kernels' stage_world(): compact the full-size tables into WT's capacities
+template <class WT>
+static void copy_world(WT& d, const DevWorld& s) {
+    memset(&d, 0, sizeof d);
+    d.n_colliders = s.n_colliders; d.n_bodies = s.n_bodies; d.n_pairs = s.n_pairs; d.n_goals = s.n_goals;
+    d.n_player_pairs = s.n_player_pairs; d.n_slots = s.n_slots;
+    d.radius = s.radius; d.half_height = s.half_height; d.lower_off = s.lower_off;
+    d.dt = s.dt; d.inv_dt = s.inv_dt; d.erp_inv_dt = s.erp_inv_dt; d.cfm_factor = s.cfm_factor;
+    d.prediction = s.prediction; d.allowed_linear_error = s.allowed_linear_error; d.aabb_margin = s.aabb_margin; d.scale = s.scale;
+    for (int c = 0; c < s.n_colliders; ++c) {
+        d.cx[c] = s.cx[c]; d.cy[c] = s.cy[c]; d.cc[c] = s.cc[c]; d.cs[c] = s.cs[c]; d.hx[c] = s.hx[c]; d.hy[c] = s.hy[c];
+        d.amnx[c] = s.amnx[c]; d.amny[c] = s.amny[c]; d.amxx[c] = s.amxx[c]; d.amxy[c] = s.amxy[c]; d.body_of[c] = s.body_of[c];
+    }
+    for (int b = 0; b < MAXB; ++b) {
+        d.inv_mass[b] = s.inv_mass[b]; d.inv_inertia_sqrt[b] = s.inv_inertia_sqrt[b]; d.ccd_thickness[b] = s.ccd_thickness[b];
+        d.gdv_x[b] = s.gdv_x[b]; d.gdv_y[b] = s.gdv_y[b]; d.collider_of[b] = s.collider_of[b];
+    }
+    for (int p = 0; p < s.n_pairs; ++p) { d.pair_c1[p] = s.pair_c1[p]; d.pair_c2[p] = s.pair_c2[p]; }
+    for (int g = 0; g < s.n_goals; ++g) {
+        d.gx[g] = s.gx[g]; d.gy[g] = s.gy[g]; d.ghw[g] = s.ghw[g]; d.ghh[g] = s.ghh[g];
+        d.gxax[g] = s.gxax[g]; d.gxay[g] = s.gxay[g]; d.gyax[g] = s.gyax[g]; d.gyay[g] = s.gyay[g];
+    }
+}
+
 extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, int genome_len, int repeat_move,
                           int number_of_steps, int early_exit, float* traj, float* score, int* win, int* steps,
                           int* overflow) {
@@ -78,11 +102,20 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
     if (rc == PRL_OK) rc = build_dev_world(&w);
     if (rc != PRL_OK) return rc;
     const DevWorld& W = w.dev;
-#define HS_ARGS W, genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow
+#define HS_ARGS genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow
     const bool small_pool = g_pool_rows < 64;
-    if (W.n_bodies == 1) *score = small_pool ? rollout<1, 32>(HS_ARGS) : rollout<1, 64>(HS_ARGS);
-    else if (W.n_bodies == 2) *score = small_pool ? rollout<2, 32>(HS_ARGS) : rollout<2, 64>(HS_ARGS);
-    else *score = small_pool ? rollout<MAXB, 32>(HS_ARGS) : rollout<MAXB, 64>(HS_ARGS);
+    // the same variant choice as the library (prl_api.cu pick_variant): small worlds run with the
+    // compact tables and slot == pair manifolds, the rest with the general tables
+    if (world_fits<DevWorldSmall>(W) && W.n_bodies <= 2) {
+        static DevWorldSmall S;
+        copy_world(S, W);
+        if (W.n_bodies == 1) *score = small_pool ? rollout<1, 32>(S, HS_ARGS) : rollout<1, 64>(S, HS_ARGS);
+        else *score = small_pool ? rollout<2, 32>(S, HS_ARGS) : rollout<2, 64>(S, HS_ARGS);
+    } else if (W.n_bodies == 1) {
+        *score = small_pool ? rollout<1, 32>(W, HS_ARGS) : rollout<1, 64>(W, HS_ARGS);
+    } else {
+        *score = small_pool ? rollout<MAXB, 32>(W, HS_ARGS) : rollout<MAXB, 64>(W, HS_ARGS);
+    }
 #undef HS_ARGS
     return 0;
 }
