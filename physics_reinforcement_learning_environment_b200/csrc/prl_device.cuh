@@ -479,6 +479,7 @@ struct Stepper {
     uint32_t active;
     uint64_t cons;      // nibble i = slot of my i-th constraint
     int ncons, need, ntb;   // constraints, rows, two-body rows (the head of the row list)
+    float im_reg[NB];       // inverse masses (registers: every row update needs one, off the critical path)
     // collision detection owed for the poses of the last position update (detect_pending)
     uint32_t pend_moved;
     bool pend_all, first_step;
@@ -486,6 +487,8 @@ struct Stepper {
         : W(w), e(env), pool(warp_pool), rbase(0), active(0), cons(0), ncons(0), need(0), ntb(0), pend_moved(0),
           pend_all((env.flags & FLAG_FRESH) != 0), first_step(false) {
         tb_g1[0] = tb_g1[1] = tb_tg1[0] = tb_tg1[1] = 0.0f;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) im_reg[b] = w.inv_mass[b];
     }
     // quad q of my row j is row_ptr(j)[q * pool_rows]
     PRL_D f4* row_ptr(int j) const {
@@ -830,25 +833,21 @@ struct Stepper {
     // increments dl* stay in registers: with one pushable block (NB == 2) a two-body row is
     // always (player, block) and a ground row selects one of two bodies.
     template <bool NORMAL>
-    PRL_D void ground_row(int j, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
-        f4* rp = row_ptr(j);
+    PRL_D void ground_row(f4* rp, bool biased, const f4& r0, const f4& r1, const f4& r2, float (&dlx)[NB], float (&dly)[NB],
+                          float (&da)[NB]) {
         const int qs = pool_rows;
-        f4 r0 = rp[0], r1 = rp[qs];
         v2 dir = V(r0.x, r0.y);
         float g2, rhs, rr, acc;
-        uint32_t bodies;
+        const uint32_t bodies = f32_bits(r2.w);
         if (NORMAL) {
             g2 = r0.z; rr = r1.y; acc = r1.z;
-            if (biased) { rhs = r1.x; bodies = f32_bits(rp[2 * qs].w); }
-            else { f4 r2 = rp[2 * qs]; rhs = r2.z; bodies = f32_bits(r2.w); }
+            rhs = biased ? r1.x : r2.z;
         } else {
-            f4 r2 = rp[2 * qs];
             dir = V(-dir.y, dir.x);  // tangent
             g2 = r0.w; rhs = r2.x; rr = r2.y; acc = r1.w;
-            bodies = f32_bits(r2.w);
         }
         int b2 = (int)((bodies >> 8) & 0xffu);
-        float im2 = W.inv_mass[b2];
+        float im2 = sel(im_reg, b2);
         v2 l2 = V(sel(dlx, b2), sel(dly, b2));
         float a2 = sel(da, b2);
         float dvel = -dot(dir, l2) + g2 * a2 + rhs;
@@ -868,6 +867,25 @@ struct Stepper {
         a2 += g2 * dl;
         put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
     }
+    // the sweep fetches the NEXT row's quads from shared memory while the current row is computed
+    // (a row's impulses are only written by its own update, so reading them one row early is safe)
+    template <bool NORMAL>
+    PRL_D void ground_rows(int jbegin, int jend, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+        if (jbegin >= jend) return;
+        const int qs = pool_rows;
+        f4* rp = row_ptr(jbegin);
+        f4 n0 = rp[0], n1 = rp[qs], n2 = rp[2 * qs];
+#pragma unroll 1
+        for (int j = jbegin; j < jend; ++j) {
+            f4 c0 = n0, c1 = n1, c2 = n2;
+            f4* cur = rp;
+            if (j + 1 < jend) {
+                rp = row_ptr(j + 1);
+                n0 = rp[0]; n1 = rp[qs]; n2 = rp[2 * qs];
+            }
+            ground_row<NORMAL>(cur, biased, c0, c1, c2, dlx, dly, da);
+        }
+    }
     template <bool NORMAL>
     PRL_D void two_body_row(int j, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
         f4* rp = row_ptr(j);
@@ -876,7 +894,7 @@ struct Stepper {
         v2 dir = V(r0.x, r0.y);
         uint32_t bodies = f32_bits(r2.w);
         int b1 = NB == 2 ? 0 : (int)(bodies & 0xffu), b2 = NB == 2 ? 1 : (int)((bodies >> 8) & 0xffu);
-        float im1 = W.inv_mass[b1], im2 = W.inv_mass[b2];
+        float im1 = sel(im_reg, b1), im2 = sel(im_reg, b2);
         float g1, g2, rhs, rr, acc;
         if (kRowQuads == 4) { f4 r3 = rp[3 * qs]; g1 = NORMAL ? r3.x : r3.y; }
         else g1 = NORMAL ? (j == 0 ? tb_g1[0] : tb_g1[1]) : (j == 0 ? tb_tg1[0] : tb_tg1[1]);
@@ -976,15 +994,13 @@ struct Stepper {
 #pragma unroll 1
                     for (int j = 0; j < ntb; ++j) two_body_row<true>(j, biased, dlx, dly, da);
                 }
-#pragma unroll 1
-                for (int j = NB > 1 ? ntb : 0; j < nrows; ++j) ground_row<true>(j, biased, dlx, dly, da);
+                ground_rows<true>(NB > 1 ? ntb : 0, nrows, biased, dlx, dly, da);
             } else {
                 if (NB > 1) {
 #pragma unroll 1
                     for (int j = 0; j < ntb; ++j) two_body_row<false>(j, biased, dlx, dly, da);
                 }
-#pragma unroll 1
-                for (int j = NB > 1 ? ntb : 0; j < nrows; ++j) ground_row<false>(j, biased, dlx, dly, da);
+                ground_rows<false>(NB > 1 ? ntb : 0, nrows, biased, dlx, dly, da);
             }
         }
 #pragma unroll
