@@ -332,10 +332,11 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
     do {                                                                                                                  \
         using Sim = Stepper<NB_, MAXC, WT_>;                                                                              \
         const size_t smem = rollout_smem_bytes<WT_, Sim::kRowQuads>(BLOCK_);                                              \
-        static bool configured = false;                                                                                   \
-        if (!configured) {                                                                                                \
+        static unsigned long long configured = 0; /* function attributes are per device */                                \
+        const unsigned long long dev_bit = 1ull << (b->device & 63);                                                      \
+        if (!(configured & dev_bit)) {                                                                                    \
             le = cudaFuncSetAttribute(rollout_kernel<NB_, WT_, BLOCK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-            configured = le == cudaSuccess;                                                                               \
+            if (le == cudaSuccess) configured |= dev_bit;                                                                 \
         }                                                                                                                 \
         if (le == cudaSuccess)                                                                                            \
             rollout_kernel<NB_, WT_, BLOCK_><<<(unsigned)((b->n + BLOCK_ - 1) / BLOCK_), BLOCK_, smem, b->stream>>>(      \
