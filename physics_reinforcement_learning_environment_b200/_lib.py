@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libprl.so")
+# PRL_LIBRARY: A/B measurements of kernel variants built beside the product library
+LIB_PATH = os.environ.get("PRL_LIBRARY") or os.path.join(_HERE, "libprl.so")
 
 PRL_OK = 0
 PRL_ERR_INVALID = -1

@@ -47,21 +47,12 @@ PRL_D int first_zero_bit(uint32_t used) {  // index of the lowest clear bit, 32 
     return 32;
 #endif
 }
-// exclusive prefix sum of v over the lanes of the warp (all 32 lanes must call it); the host
-// build is a single "lane"
-PRL_D int warp_exclusive_sum(int v, int& total) {
+// maximum of v over the lanes of the warp (all 32 lanes must call it); the host build is a single "lane"
+PRL_D int warp_max(int v) {
 #if defined(__CUDA_ARCH__)
-    int incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int up = __shfl_up_sync(0xffffffffu, incl, o);
-        if ((int)(threadIdx.x & 31u) >= o) incl += up;
-    }
-    total = __shfl_sync(0xffffffffu, incl, 31);
-    return incl - v;
+    return (int)__reduce_max_sync(0xffffffffu, (unsigned)v);
 #else
-    total = v;
-    return 0;
+    return v;
 #endif
 }
 PRL_D int first_bit_from(uint32_t mask, int from) {  // lowest set bit at or above `from`, 32 if none
@@ -450,52 +441,68 @@ struct Env {
     f4 sc[S][2];
 };
 
-template <int NB, int S, class WT = DevWorld, int POOL_ROWS = 64>
+struct alignas(8) f2 { float x, y; };
+
+template <int NB, int S, class WT = DevWorld, int CAP = 8>
 struct Stepper {
     using E = Env<NB, S>;
     static constexpr int kGround = NB;  // pseudo body index of the fixed world: zero velocity, zero inverse mass
-    // Velocity-constraint rows, one per solver contact, in Gauss-Seidel order (per-step scratch),
-    // as 16-byte quads:
-    //   quad 0 = (dir.x, dir.y, gcross2, t_gcross2)
-    //   quad 1 = (rhs, r, normal impulse, tangent impulse)
-    //   quad 2 = (t_rhs, t_r, rhs_wo_bias, bodies)   bodies bits = body1 | body2 << 8 | fast << 16
-    //   quad 3 = (gcross1, t_gcross1, -, -)          body 1's angular terms, two-body rows only
+    // Velocity-constraint rows, one per solver contact, in Gauss-Seidel order (per-step scratch).
+    // The 14 solver sweeps re-read every row, so rows live in shared memory, and the shared-memory
+    // data pipe is what bounds the sweeps: a row is therefore split into planes that are each
+    // read with the widest conflict-free access, and a lane's rows sit in the lane's own COLUMN
+    // (entry = row * 32 + lane), so that every access of a warp covers consecutive addresses:
+    //   plane 0  f4  (dir.x, dir.y, gcross2, t_gcross2)                  both sweeps
+    //   plane 1  f4  (rhs, r, rhs_wo_bias, bits)                         normal sweeps
+    //                bits = body1 | body2 << 8 | fast << 16
+    //   plane 2  f2  (t_rhs, t_r)                                        friction sweeps
+    //   plane 3  f   accumulated normal impulse                          read + written
+    //   plane 4  f   accumulated tangent impulse                         read + written
+    //   plane 5  f2  (gcross1, t_gcross1)  body 1's angular terms        only with NB > 2
     // With at most one pushable block (NB <= 2) the only two-body rows are the <= 2 rows of the
-    // player-block manifold, whose quad 3 stays in registers (tb_g1 / tb_tg1): rows are 48 bytes.
-    // The 14 solver sweeps re-read every row and their working set per SM exceeds L1, so rows
-    // live in shared memory: each warp owns a pool of `pool_rows` rows (kRowQuads planes of
-    // quads, XOR-swizzled against bank conflicts), handed out every step by a warp prefix sum
-    // over the lanes' row counts -- the average environment needs far fewer rows than the worst
-    // case. If a warp's rows do not all fit, its lanes solve in rounds (see the kernels).
-    static constexpr int kRowQuads = NB <= 2 ? 3 : 4;
-    static constexpr int kMaxRows = 2 * S;  // rows one environment can need; pool_rows must be >= this
+    // player-block manifold, whose plane 5 stays in registers (tb_g1 / tb_tg1), and a ground
+    // row's body follows from its position in the row list (player pairs sort first).
+    // A column holds CAP rows. An environment that needs more borrows the columns of its
+    // neighbours: the warp then solves in G rounds, lane l owning columns [l & ~(G-1), +G) in
+    // round l & (G-1) (see the kernels); G == 1 in all but a fraction of a percent of the steps.
+    static constexpr int kCap = CAP;
+    static constexpr int kCapLog2 = CAP == 4 ? 2 : 3;
+    static_assert(CAP == 4 || CAP == 8, "column height must be 4 or 8 rows");
+    static constexpr int kEntries = 32 * CAP;   // entries per plane per warp
+    static constexpr int kRowBytes = 48 + (NB > 2 ? 8 : 0);
+    static constexpr int kWarpBytes = kEntries * kRowBytes;
+    static constexpr int kOff1 = 16 * kEntries, kOff2 = 32 * kEntries, kOff3 = 40 * kEntries, kOff4 = 44 * kEntries,
+                         kOff5 = 48 * kEntries;
+    static constexpr int kMaxRows = 2 * S;  // rows one environment can need
+    static_assert(kMaxRows <= 8 * CAP, "eight columns must hold every row of one environment");
     const WT& W;
     E& e;
-    f4* pool;
-    static constexpr int pool_rows = POOL_ROWS;  // rows in the warp's pool (plane stride, in quads)
-    int rbase;          // first pool row of this lane, this step
+    unsigned char* pool;    // the warp's planes
+    int col;                // first column of this lane, this step
     float tb_g1[2], tb_tg1[2];
     // constraint selection of the current step (begin_step -> finish_step)
     uint32_t active;
     uint64_t cons;      // nibble i = slot of my i-th constraint
-    int ncons, need, ntb;   // constraints, rows, two-body rows (the head of the row list)
+    int ncons, need, ntb, nplayer;   // constraints, rows, two-body rows (the head of the row list), rows of player pairs
     float im_reg[NB];       // inverse masses (registers: every row update needs one, off the critical path)
     // collision detection owed for the poses of the last position update (detect_pending)
     uint32_t pend_moved;
     bool pend_all, first_step;
-    PRL_D Stepper(const WT& w, E& env, f4* warp_pool)
-        : W(w), e(env), pool(warp_pool), rbase(0), active(0), cons(0), ncons(0), need(0), ntb(0), pend_moved(0),
-          pend_all((env.flags & FLAG_FRESH) != 0), first_step(false) {
+    PRL_D Stepper(const WT& w, E& env, void* warp_pool)
+        : W(w), e(env), pool(static_cast<unsigned char*>(warp_pool)), col(0), active(0), cons(0), ncons(0), need(0), ntb(0),
+          nplayer(0), pend_moved(0), pend_all((env.flags & FLAG_FRESH) != 0), first_step(false) {
         tb_g1[0] = tb_g1[1] = tb_tg1[0] = tb_tg1[1] = 0.0f;
 #pragma unroll
         for (int b = 0; b < NB; ++b) im_reg[b] = w.inv_mass[b];
     }
-    // quad q of my row j is row_ptr(j)[q * pool_rows]
-    PRL_D f4* row_ptr(int j) const {
-        int g = rbase + j;
-        return pool + (g ^ ((g >> 3) & 7));
-    }
-    PRL_D int row_qstride() const { return pool_rows; }
+    // entry of my row j: row j % CAP of column col + j / CAP
+    PRL_D int row_entry(int j) const { return ((j & (CAP - 1)) << 5) + col + (j >> kCapLog2); }
+    PRL_D f4& q0(int en) const { return reinterpret_cast<f4*>(pool)[en]; }
+    PRL_D f4& q1(int en) const { return reinterpret_cast<f4*>(pool + kOff1)[en]; }
+    PRL_D f2& q2(int en) const { return reinterpret_cast<f2*>(pool + kOff2)[en]; }
+    PRL_D float& acc_n(int en) const { return reinterpret_cast<float*>(pool + kOff3)[en]; }
+    PRL_D float& acc_t(int en) const { return reinterpret_cast<float*>(pool + kOff4)[en]; }
+    PRL_D f2& q5(int en) const { return reinterpret_cast<f2*>(pool + kOff5)[en]; }
 
     // slot == pair index. (Single-body worlds measured 7 % faster with the sorted list: they rarely
     // hold more than two manifolds.)
@@ -777,7 +784,7 @@ struct Stepper {
             v2 dp1 = pt - com1, dp2 = pt - com2;
             v2 vel1 = v1 + wcross(w1, dp1);
             v2 vel2 = v2_ + wcross(w2, dp2);
-            f4 r0, r1, r2, r3;
+            f4 r0, r1;
             float gcross2 = ii2 * cross(dp2, -dir1);
             float gcross1 = 0.0f, pm;
             if (NB > 1 && two_body) {
@@ -806,15 +813,17 @@ struct Stepper {
             }
             v2 dv = (vel1 - vel2) + V(0.0f, 0.0f);
             r0.x = dir1.x; r0.y = dir1.y; r0.z = gcross2; r0.w = t_gcross2;
-            r1.x = rhs; r1.y = pm; r1.z = 0.0f; r1.w = 0.0f;
-            r2.x = dot(dv, tan1); r2.y = inv0(tr); r2.z = rhs_wo_bias; r2.w = bits_f32(bodies);
+            r1.x = rhs; r1.y = pm; r1.z = rhs_wo_bias; r1.w = bits_f32(bodies);
+            f2 r2;
+            r2.x = dot(dv, tan1); r2.y = inv0(tr);
             int j = nrows + k;
-            f4* rp = row_ptr(j);
-            int qs = row_qstride();
-            rp[0] = r0; rp[qs] = r1; rp[2 * qs] = r2;
-            if (kRowQuads == 4) {
-                r3.x = gcross1; r3.y = t_gcross1; r3.z = 0.0f; r3.w = 0.0f;
-                rp[3 * qs] = r3;
+            int en = row_entry(j);
+            q0(en) = r0; q1(en) = r1; q2(en) = r2;
+            acc_n(en) = 0.0f; acc_t(en) = 0.0f;
+            if (NB > 2) {
+                f2 r5;
+                r5.x = gcross1; r5.y = t_gcross1;
+                q5(en) = r5;
             } else if (NB == 2 && two_body) {
                 if (j == 0) { tb_g1[0] = gcross1; tb_tg1[0] = t_gcross1; }
                 else { tb_g1[1] = gcross1; tb_tg1[1] = t_gcross1; }
@@ -822,7 +831,7 @@ struct Stepper {
         }
         if (fast) {  // a fast contact makes the whole constraint rigid (cfm_factor 1)
 #pragma unroll 1
-            for (int k = 0; k < ns; ++k) row_ptr(nrows + k)[2 * row_qstride()].w = bits_f32(bodies | (1u << 16));
+            for (int k = 0; k < ns; ++k) q1(row_entry(nrows + k)).w = bits_f32(bodies | (1u << 16));
         }
         return nrows + ns;
     }
@@ -830,76 +839,105 @@ struct Stepper {
     // Gauss-Seidel row updates: rapier VelocityConstraintElement::solve_group (two bodies) and
     // VelocityGroundConstraintElement::solve_group (one body), normal part and friction part.
     // Two-body rows come first in the row list (ntb of them), ground rows after. The body
-    // increments dl* stay in registers: with one pushable block (NB == 2) a two-body row is
-    // always (player, block) and a ground row selects one of two bodies.
-    template <bool NORMAL>
-    PRL_D void ground_row(f4* rp, bool biased, const f4& r0, const f4& r1, const f4& r2, float (&dlx)[NB], float (&dly)[NB],
-                          float (&da)[NB]) {
-        const int qs = pool_rows;
-        v2 dir = V(r0.x, r0.y);
-        float g2, rhs, rr, acc;
-        const uint32_t bodies = f32_bits(r2.w);
-        if (NORMAL) {
-            g2 = r0.z; rr = r1.y; acc = r1.z;
-            rhs = biased ? r1.x : r2.z;
-        } else {
-            dir = V(-dir.y, dir.x);  // tangent
-            g2 = r0.w; rhs = r2.x; rr = r2.y; acc = r1.w;
-        }
-        int b2 = (int)((bodies >> 8) & 0xffu);
-        float im2 = sel(im_reg, b2);
-        v2 l2 = V(sel(dlx, b2), sel(dly, b2));
-        float a2 = sel(da, b2);
+    // increments dl* stay in registers. BODY >= 0: every row of the range acts on that body (with
+    // one pushable block the ground rows of the player's pairs precede the block's, so the sweep
+    // is two ranges with a compile-time body); BODY < 0: the body comes from the row's bits.
+    // The sweep fetches the NEXT row from shared memory while the current row is computed (a
+    // row's impulses are only written by its own update, so reading them one row early is safe).
+    struct RowN { f4 a, b; float acc; };            // plane 0, plane 1, normal impulse
+    struct RowT { f4 a; f2 c; float acc, accn; uint32_t bits; };  // plane 0, plane 2, tangent impulse, normal impulse
+    PRL_D void fetch(int en, RowN& r) const { r.a = q0(en); r.b = q1(en); r.acc = acc_n(en); }
+    template <int BODY> PRL_D void fetch(int en, RowT& r) const {
+        r.a = q0(en); r.c = q2(en); r.acc = acc_t(en); r.accn = acc_n(en);
+        r.bits = BODY < 0 ? f32_bits(q1(en).w) : 0u;
+    }
+    template <int BODY>
+    PRL_D void ground_row_n(int en, bool biased, const RowN& r, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+        const v2 dir = V(r.a.x, r.a.y);
+        const float g2 = r.a.z, rr = r.b.y, acc = r.acc;
+        const float rhs = biased ? r.b.x : r.b.z;
+        const uint32_t bits = f32_bits(r.b.w);
+        const int b2 = BODY >= 0 ? BODY : (int)((bits >> 8) & 0xffu);
+        const float im2 = BODY >= 0 ? im_reg[BODY >= 0 ? BODY : 0] : sel(im_reg, b2);
+        v2 l2 = BODY >= 0 ? V(dlx[BODY >= 0 ? BODY : 0], dly[BODY >= 0 ? BODY : 0]) : V(sel(dlx, b2), sel(dly, b2));
+        float a2 = BODY >= 0 ? da[BODY >= 0 ? BODY : 0] : sel(da, b2);
         float dvel = -dot(dir, l2) + g2 * a2 + rhs;
-        float ni;
-        if (NORMAL) {
-            // the stabilisation sweep runs without the penetration bias and without softness
-            float cfm = (biased && !(bodies >> 16)) ? W.cfm_factor : 1.0f;
-            ni = cfm * fmaxf(acc - rr * dvel, 0.0f);
-            rp[qs].z = ni;
-        } else {
-            float limit = kFriction * r1.z;
-            ni = fminf(fmaxf(acc - rr * dvel, -limit), limit);
-            rp[qs].w = ni;
-        }
+        // the stabilisation sweep runs without the penetration bias and without softness
+        float cfm = (biased && !(bits >> 16)) ? W.cfm_factor : 1.0f;
+        float ni = cfm * fmaxf(acc - rr * dvel, 0.0f);
+        acc_n(en) = ni;
         float dl = ni - acc;
         l2 = l2 + (dir * im2) * -dl;
         a2 += g2 * dl;
-        put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
+        if (BODY >= 0) { dlx[BODY >= 0 ? BODY : 0] = l2.x; dly[BODY >= 0 ? BODY : 0] = l2.y; da[BODY >= 0 ? BODY : 0] = a2; }
+        else { put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2); }
     }
-    // the sweep fetches the NEXT row's quads from shared memory while the current row is computed
-    // (a row's impulses are only written by its own update, so reading them one row early is safe)
-    template <bool NORMAL>
+    template <int BODY>
+    PRL_D void ground_row_t(int en, const RowT& r, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+        const v2 dir = V(-r.a.y, r.a.x);  // tangent
+        const float g2 = r.a.w, rhs = r.c.x, rr = r.c.y, acc = r.acc;
+        const int b2 = BODY >= 0 ? BODY : (int)((r.bits >> 8) & 0xffu);
+        const float im2 = BODY >= 0 ? im_reg[BODY >= 0 ? BODY : 0] : sel(im_reg, b2);
+        v2 l2 = BODY >= 0 ? V(dlx[BODY >= 0 ? BODY : 0], dly[BODY >= 0 ? BODY : 0]) : V(sel(dlx, b2), sel(dly, b2));
+        float a2 = BODY >= 0 ? da[BODY >= 0 ? BODY : 0] : sel(da, b2);
+        float dvel = -dot(dir, l2) + g2 * a2 + rhs;
+        float limit = kFriction * r.accn;
+        float ni = fminf(fmaxf(acc - rr * dvel, -limit), limit);
+        acc_t(en) = ni;
+        float dl = ni - acc;
+        l2 = l2 + (dir * im2) * -dl;
+        a2 += g2 * dl;
+        if (BODY >= 0) { dlx[BODY >= 0 ? BODY : 0] = l2.x; dly[BODY >= 0 ? BODY : 0] = l2.y; da[BODY >= 0 ? BODY : 0] = a2; }
+        else { put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2); }
+    }
+    template <bool NORMAL, int BODY>
     PRL_D void ground_rows(int jbegin, int jend, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
         if (jbegin >= jend) return;
-        const int qs = pool_rows;
-        f4* rp = row_ptr(jbegin);
-        f4 n0 = rp[0], n1 = rp[qs], n2 = rp[2 * qs];
+        int en = row_entry(jbegin);
+        if (NORMAL) {
+            RowN nx;
+            fetch(en, nx);
 #pragma unroll 1
-        for (int j = jbegin; j < jend; ++j) {
-            f4 c0 = n0, c1 = n1, c2 = n2;
-            f4* cur = rp;
-            if (j + 1 < jend) {
-                rp = row_ptr(j + 1);
-                n0 = rp[0]; n1 = rp[qs]; n2 = rp[2 * qs];
+            for (int j = jbegin; j < jend; ++j) {
+                const RowN cur = nx;
+                const int cen = en;
+                en = row_entry(j + 1 < jend ? j + 1 : j);  // the last iteration re-reads its own row: no branch
+                fetch(en, nx);
+                ground_row_n<BODY>(cen, biased, cur, dlx, dly, da);
             }
-            ground_row<NORMAL>(cur, biased, c0, c1, c2, dlx, dly, da);
+        } else {
+            RowT nx;
+            fetch<BODY>(en, nx);
+#pragma unroll 1
+            for (int j = jbegin; j < jend; ++j) {
+                const RowT cur = nx;
+                const int cen = en;
+                en = row_entry(j + 1 < jend ? j + 1 : j);
+                fetch<BODY>(en, nx);
+                ground_row_t<BODY>(cen, cur, dlx, dly, da);
+            }
         }
     }
     template <bool NORMAL>
     PRL_D void two_body_row(int j, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
-        f4* rp = row_ptr(j);
-        const int qs = pool_rows;
-        f4 r0 = rp[0], r1 = rp[qs], r2 = rp[2 * qs];
+        const int en = row_entry(j);
+        const f4 r0 = q0(en);
         v2 dir = V(r0.x, r0.y);
-        uint32_t bodies = f32_bits(r2.w);
+        uint32_t bodies = 0;
+        float g1, g2, rhs, rr, acc, accn = 0.0f;
+        if (NORMAL) {
+            const f4 r1 = q1(en);
+            bodies = f32_bits(r1.w);
+            g2 = r0.z; rr = r1.y; rhs = biased ? r1.x : r1.z; acc = acc_n(en);
+        } else {
+            const f2 r2 = q2(en);
+            if (NB > 2) bodies = f32_bits(q1(en).w);
+            dir = V(-dir.y, dir.x); g2 = r0.w; rhs = r2.x; rr = r2.y; acc = acc_t(en); accn = acc_n(en);
+        }
         int b1 = NB == 2 ? 0 : (int)(bodies & 0xffu), b2 = NB == 2 ? 1 : (int)((bodies >> 8) & 0xffu);
         float im1 = sel(im_reg, b1), im2 = sel(im_reg, b2);
-        float g1, g2, rhs, rr, acc;
-        if (kRowQuads == 4) { f4 r3 = rp[3 * qs]; g1 = NORMAL ? r3.x : r3.y; }
+        if (NB > 2) { const f2 r5 = q5(en); g1 = NORMAL ? r5.x : r5.y; }
         else g1 = NORMAL ? (j == 0 ? tb_g1[0] : tb_g1[1]) : (j == 0 ? tb_tg1[0] : tb_tg1[1]);
-        if (NORMAL) { g2 = r0.z; rr = r1.y; acc = r1.z; rhs = biased ? r1.x : r2.z; }
-        else { dir = V(-dir.y, dir.x); g2 = r0.w; rhs = r2.x; rr = r2.y; acc = r1.w; }
         v2 l1 = V(sel(dlx, b1), sel(dly, b1)), l2 = V(sel(dlx, b2), sel(dly, b2));
         float a1 = sel(da, b1), a2 = sel(da, b2);
         float dvel = dot(dir, l1) + g1 * a1 - dot(dir, l2) + g2 * a2 + rhs;
@@ -907,11 +945,11 @@ struct Stepper {
         if (NORMAL) {
             float cfm = (biased && !(bodies >> 16)) ? W.cfm_factor : 1.0f;
             ni = cfm * fmaxf(acc - rr * dvel, 0.0f);
-            rp[qs].z = ni;
+            acc_n(en) = ni;
         } else {
-            float limit = kFriction * r1.z;
+            float limit = kFriction * accn;
             ni = fminf(fmaxf(acc - rr * dvel, -limit), limit);
-            rp[qs].w = ni;
+            acc_t(en) = ni;
         }
         float dl = ni - acc;
         l1 = l1 + (dir * im1) * dl;
@@ -932,6 +970,7 @@ struct Stepper {
         ncons = 0;
         need = 0;
         ntb = 0;
+        nplayer = 0;
 #pragma unroll 1
         for (int pass = NB == 1 ? 1 : 0; pass < 2; ++pass) {
 #pragma unroll 1
@@ -950,15 +989,16 @@ struct Stepper {
                 ++ncons;
                 need += ns;
                 if (two_body) ntb += ns;
+                else if (p < W.n_player_pairs) nplayer += ns;
             }
         }
     }
 
     // constraint build + VelocitySolver::solve + position update for the active bodies (SURVEY
-    // A.3 stages 4-7), with this lane's rows starting at pool row `base`. Returns the mask of
-    // bodies that moved.
-    PRL_D uint32_t solve_and_integrate(int base) {
-        rbase = base;
+    // A.3 stages 4-7), with this lane's rows in the warp's columns [first_col, ...). Returns the
+    // mask of bodies that moved.
+    PRL_D uint32_t solve_and_integrate(int first_col) {
+        col = first_col;
         int nrows = 0;
 #pragma unroll 1
         for (int i = 0; i < ncons; ++i) nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows);
@@ -989,18 +1029,28 @@ struct Stepper {
                 }
             }
             const bool biased = sweep < 12;
+            // ground rows: rows [ntb, jsplit) belong to the player's pairs, [jsplit, nrows) to block pairs
+            const int jsplit = ntb + nplayer;
             if (sweep == 12 || (sweep < 8 && (sweep & 1) == 0)) {
                 if (NB > 1) {
 #pragma unroll 1
                     for (int j = 0; j < ntb; ++j) two_body_row<true>(j, biased, dlx, dly, da);
                 }
-                ground_rows<true>(NB > 1 ? ntb : 0, nrows, biased, dlx, dly, da);
+                if (NB == 1) ground_rows<true, 0>(0, nrows, biased, dlx, dly, da);
+                else if (NB == 2) {
+                    ground_rows<true, 0>(ntb, jsplit, biased, dlx, dly, da);
+                    ground_rows<true, 1>(jsplit, nrows, biased, dlx, dly, da);
+                } else ground_rows<true, -1>(ntb, nrows, biased, dlx, dly, da);
             } else {
                 if (NB > 1) {
 #pragma unroll 1
                     for (int j = 0; j < ntb; ++j) two_body_row<false>(j, biased, dlx, dly, da);
                 }
-                ground_rows<false>(NB > 1 ? ntb : 0, nrows, biased, dlx, dly, da);
+                if (NB == 1) ground_rows<false, 0>(0, nrows, biased, dlx, dly, da);
+                else if (NB == 2) {
+                    ground_rows<false, 0>(ntb, jsplit, biased, dlx, dly, da);
+                    ground_rows<false, 1>(jsplit, nrows, biased, dlx, dly, da);
+                } else ground_rows<false, -1>(ntb, nrows, biased, dlx, dly, da);
             }
         }
 #pragma unroll
@@ -1224,8 +1274,8 @@ struct Stepper {
     //
     //   detect_pending();                 // broad + narrow phase owed by the previous position update
     //   need = begin_step(move);          // ground scan + move impulses + constraint selection
-    //   base = warp_exclusive_sum(need);  // (kernel) rows from the warp's pool
-    //   d = finish_step(base);            // solve, integrate, win latch
+    //   (kernel) the warp agrees on how many columns of row storage a lane gets this step
+    //   d = finish_step(first column);    // solve, integrate, win latch
     //
     // rapier runs the detection at the END of PhysicsPipeline::step; running it at the start of
     // the next step (and once more after the last one) is the same sequence of operations.
@@ -1247,8 +1297,8 @@ struct Stepper {
         select_constraints();
         return need;
     }
-    PRL_D float finish_step(int base) {
-        pend_moved = solve_and_integrate(base);
+    PRL_D float finish_step(int first_col) {
+        pend_moved = solve_and_integrate(first_col);
         // query_pipeline.update (common.rs:330-331) is never queried: omitted
         float d = distance_to_goals();
         if (!(e.flags & FLAG_WON) && W.n_goals > 0 && d < 1e-7f) e.flags |= FLAG_WON;
@@ -1258,9 +1308,8 @@ struct Stepper {
     // the last step
     PRL_D float step(uint32_t mv) {
         detect_pending();
-        int want = begin_step(mv), total;
-        int base = warp_exclusive_sum(want, total);
-        return finish_step(base);
+        begin_step(mv);
+        return finish_step(0);  // a single lane owns every column
     }
 };
 

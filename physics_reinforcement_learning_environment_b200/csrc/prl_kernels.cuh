@@ -15,12 +15,13 @@
 namespace prl {
 
 constexpr int kBlock = 64;
-// Shared-memory budget of a 64-thread block: the world tables plus one pool of velocity-constraint
-// rows per warp (prl_device.cuh, Stepper). A 65536-environment batch puts 7 blocks on each SM, so
-// a block may use 227 KB / 7 = 32.4 KB: 15 KB of rows per warp beside the 1 KB tables of a small
-// world (320 rows of 48 B), 12 KB beside the 6.1 KB full-size tables.
-template <class WT> struct PoolBytes { static constexpr int value = 12288; };
-template <> struct PoolBytes<DevWorldSmall> { static constexpr int value = 15360; };
+// Shared memory of a block: the world tables plus, per warp, the planes of velocity-constraint
+// rows (prl_device.cuh, Stepper): 32 columns of kRowCap rows. Single-body worlds rarely need more
+// than two rows per environment and get 4-row columns (6 KB per warp); worlds with pushable blocks
+// get 8-row columns (12 KB per warp, 14 KB with more than one pushable block). A 65536-environment
+// batch puts 7 64-thread blocks (or one 448-thread block) on each SM.
+template <int NB> struct RowCap { static constexpr int value = NB == 1 ? 4 : 8; };
+template <int NB, class WT> using SimOf = Stepper<NB, MAXC, WT, RowCap<NB>::value>;
 // Rollouts of large batches run ONE block of 448 threads per SM (the same 14 warps, 148 x 448 >=
 // 65536) with a block barrier at the top of every step: the step is ~4000 straight-line
 // instructions outside the solver's loops, and warps of one SM that are in the same phase of the
@@ -35,9 +36,30 @@ constexpr int kBigBlock = 448;
 constexpr int kRegroupEvery = 64;
 constexpr int kRegroupKeys = 34;  // 0 = finished, 1 + min(rows, 32)
 constexpr size_t kRegroupBytes = (kRegroupKeys + 2 * kBigBlock) * sizeof(int);
-template <class WT, int RQ>
+template <int NB, class WT>
 constexpr size_t rollout_smem_bytes(int block) {
-    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * PoolBytes<WT>::value + (block == kBigBlock ? kRegroupBytes : 0);
+    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * SimOf<NB, WT>::kWarpBytes + (block == kBigBlock ? kRegroupBytes : 0);
+}
+
+// One step's solve for the lanes of a warp. The warp first agrees on how many columns of row
+// storage a lane gets: G = 1 unless some environment needs more rows than a column holds, in
+// which case lanes take turns in G rounds, lane l using the G columns of its group in round
+// l % G. `body(first_col)` runs finish_step and the caller's bookkeeping. Every lane of the warp
+// must call this (lanes with nothing to do pass run = false, need = 0).
+template <class SIM, class F>
+__device__ __forceinline__ void solve_in_rounds(bool run, int need, F&& body) {
+    const int mx = warp_max(need);
+    const int lane = (int)(threadIdx.x & 31u);
+    if (mx <= SIM::kCap) {
+        if (run) body(lane);
+        return;
+    }
+    const int G = mx <= 2 * SIM::kCap ? 2 : (mx <= 4 * SIM::kCap ? 4 : 8);
+#pragma unroll 1
+    for (int r = 0; r < G; ++r) {
+        if (run && (lane & (G - 1)) == r) body(lane & ~(G - 1));
+        __syncwarp();
+    }
 }
 
 // block-wide copy of the world tables into shared memory (compacting into WT's capacities)
@@ -113,7 +135,7 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, const uint32_t
     // live manifolds are stored compacted in pair order: HBM slot k = k-th manifold. The 15 HBM
     // words of a slot are the first 15 words of the 16-word thread-local record. Small worlds
     // keep the manifold of pair p in record p (Stepper::kDirect), larger ones in record k.
-    constexpr bool direct = Stepper<NB, MAXC, WT>::kDirect;
+    constexpr bool direct = SimOf<NB, WT>::kDirect;
     int base = F_DYN + 8 * (W.n_bodies - 1);
     const int count = e.count;
     e.order = 0xfedcba9876543210ull;
@@ -136,7 +158,7 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, const uint32_t
 template <int NB, class WT>
 __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto sf = [&](int f, float v) { st[(int64_t)f * n + i] = __float_as_uint(v); };
-    constexpr bool direct = Stepper<NB, MAXC, WT>::kDirect;
+    constexpr bool direct = SimOf<NB, WT>::kDirect;
     int count = direct ? __popc(e.used) : e.count;
     count = count < W.n_slots ? count : W.n_slots;
     st[(int64_t)F_FLAGS * n + i] = (e.sleeping & 0xffu) | e.flags | ((uint32_t)count << 16);
@@ -187,18 +209,16 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const DevWorld* __restric
 // n_steps == 1; else `uniform_move` for all, n_steps times. Also maintains the running minimum of
 // distance_to_goals, the step of the first win and the step counter.
 template <int NB, class WT>
-__global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+__global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) step_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                       const uint8_t* __restrict__ moves, uint32_t uniform_move, int n_steps,
                                                       int* __restrict__ overflow) {
-    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Stepper<NB, MAXC, WT>::kRowQuads);
-    using Sim = Stepper<NB, MAXC, WT, kPoolRows>;
-    static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
+    using Sim = SimOf<NB, WT>;
     __shared__ WT W;
-    __shared__ f4 row_pool[(kBlock / 32) * Sim::kRowQuads * kPoolRows];
+    __shared__ __align__(16) unsigned char row_pool[(kBlock / 32) * Sim::kWarpBytes];
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // the row pool is handed out with warp shuffles, so every lane stays alive: lanes past the
-    // end replay the last environment and skip the stores
+    // the warp agrees on its row storage with a warp vote every step, so every lane stays alive:
+    // lanes past the end replay the last environment and skip the stores
     const bool live = i < n;
     if (!live) i = n - 1;
     Env<NB> e;
@@ -207,27 +227,19 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restr
     int win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
     int steps = (int)st[(int64_t)F_STEPS * n + i];
     uint32_t mv = moves ? (moves[i] & 7u) : (uniform_move & 7u);
-    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows);
+    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     sim.refresh_solver_contacts();
 #pragma unroll 1
     for (int t = 0;; ++t) {
         sim.detect_pending();
         if (t == n_steps) break;
         const int need = sim.begin_step(mv);
-        bool pending = true;
-#pragma unroll 1
-        while (true) {  // rounds: normally one -- every lane's rows fit the warp's pool
-            int total;
-            int base = warp_exclusive_sum(pending ? need : 0, total);
-            if (pending && base + need <= kPoolRows) {
-                float d = sim.finish_step(base);
-                ++steps;
-                score = fminf(score, d);
-                if ((e.flags & FLAG_WON) && win_step < 0) win_step = steps;
-                pending = false;
-            }
-            if (total <= kPoolRows) break;
-        }
+        solve_in_rounds<Sim>(true, need, [&](int first_col) {
+            float d = sim.finish_step(first_col);
+            ++steps;
+            score = fminf(score, d);
+            if ((e.flags & FLAG_WON) && win_step < 0) win_step = steps;
+        });
     }
     if (!live) return;
     if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);  // more live manifolds than PRL_MAX_CONTACTS: reported by prl_batch_sync
@@ -242,38 +254,36 @@ __global__ void __launch_bounds__(kBlock, 7) step_kernel(const DevWorld* __restr
 // distance_to_goals. early_exit reproduces the reference's break-on-win (including the tail's
 // extra step after a win); without it every step is executed (throughput runs).
 template <int NB, class WT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : 7) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+__global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 7)) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                          const uint8_t* __restrict__ genomes, int genome_len, int repeat_move,
                                                          int number_of_steps, int early_exit,
                                                          float* __restrict__ out_score, int32_t* __restrict__ out_win,
                                                          int* __restrict__ overflow) {
-    constexpr int kPoolRows = PoolBytes<WT>::value / (16 * Stepper<NB, MAXC, WT>::kRowQuads);
-    using Sim = Stepper<NB, MAXC, WT, kPoolRows>;
-    static_assert(kPoolRows >= Sim::kMaxRows && kPoolRows % 8 == 0, "a lane's rows must fit the pool on their own");
+    using Sim = SimOf<NB, WT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WT& W = *reinterpret_cast<WT*>(smem_raw);
-    f4* row_pool = reinterpret_cast<f4*>(smem_raw + ((sizeof(WT) + 15) / 16) * 16);
+    unsigned char* row_pool = smem_raw + ((sizeof(WT) + 15) / 16) * 16;
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n;  // see step_kernel
     if (!live) i = n - 1;
     Env<NB> e;
     env_init(W, e);
-    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kRowQuads * kPoolRows);
+    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     float score = __int_as_float(0x7f800000);
     int win_step = -1, steps = 0;
     const uint8_t* genome = genomes + i * (int64_t)genome_len;
     // one flat loop over the gene phase (genome_len x repeat_move steps) and the tail phase
     // (number_of_steps % repeat_move default moves): a win in the gene phase skips to the tail,
     // which then runs one more step before it sees won() -- the reference's two loops. A lane
-    // whose rollout has ended idles in the loop until the whole block is done: the warp hands
-    // out the solver's row pool collectively every step, and the block barrier at the top of the
-    // step keeps the SM's warps in the same phase of the step (shared instruction fetches).
+    // whose rollout has ended idles in the loop until the whole block is done: the warp votes on
+    // its row storage every step, and the block barrier at the top of the step keeps the SM's
+    // warps in the same phase of the step (shared instruction fetches).
     const int main_steps = genome_len * repeat_move;
     const int total = main_steps + number_of_steps % repeat_move;
     int g = 0, rep = 0, t = 0, iter = 0;
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
-    int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kRowQuads * kPoolRows);  // only if BLOCK == kBigBlock
+    int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes);  // only if BLOCK == kBigBlock
 #pragma unroll 1
     while (true) {
         sim.detect_pending();
@@ -318,27 +328,19 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : 7) rollout_ker
         const bool run = t < total;
         const bool in_genes = t < main_steps;
         const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
-        bool pending = run;
-#pragma unroll 1
-        while (true) {  // rounds: normally one -- every lane's rows fit the warp's pool
-            int pool_total;
-            int base = warp_exclusive_sum(pending ? need : 0, pool_total);
-            if (pending && base + need <= kPoolRows) {
-                float d = sim.finish_step(base);
-                ++steps;
-                ++t;
-                score = fminf(score, d);
-                bool won = (e.flags & FLAG_WON) != 0;
-                if (won && win_step < 0) win_step = steps;
-                if (in_genes && ++rep == repeat_move) {
-                    rep = 0;
-                    if (++g < genome_len) gene = genome[g] & 7u;
-                }
-                if (won && early_exit) t = in_genes ? main_steps : total;
-                pending = false;
+        solve_in_rounds<Sim>(run, need, [&](int first_col) {
+            float d = sim.finish_step(first_col);
+            ++steps;
+            ++t;
+            score = fminf(score, d);
+            bool won = (e.flags & FLAG_WON) != 0;
+            if (won && win_step < 0) win_step = steps;
+            if (in_genes && ++rep == repeat_move) {
+                rep = 0;
+                if (++g < genome_len) gene = genome[g] & 7u;
             }
-            if (pool_total <= kPoolRows) break;
-        }
+            if (won && early_exit) t = in_genes ? main_steps : total;
+        });
     }
     if (!live) return;
     if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);  // more live manifolds than PRL_MAX_CONTACTS: reported by prl_batch_sync

@@ -10,8 +10,22 @@
 
 using namespace prl;
 
-static int g_pool_rows = 64;
-extern "C" void hs_set_pool_rows(int rows) { g_pool_rows = rows < 32 ? 32 : (rows > 64 ? 64 : rows); }
+static int g_row_cap = 8;
+// statistics for sizing the kernels' row storage: histogram of solver rows per environment step,
+// and of two-body rows / body-0 ground rows
+static long g_need_hist[3][40];
+extern "C" void hs_need_hist(long* out, int reset) {
+    memcpy(out, g_need_hist, sizeof g_need_hist);
+    if (reset) memset(g_need_hist, 0, sizeof g_need_hist);
+}
+template <class SIM> static void count_need(const SIM& sim) {
+    ++g_need_hist[0][sim.need < 39 ? sim.need : 39];
+    ++g_need_hist[1][sim.ntb < 39 ? sim.ntb : 39];
+    int live = sim.live_count();
+    ++g_need_hist[2][live < 39 ? live : 39];
+}
+// rows per column of the solver's row storage (4 or 8): the layout must not change any result
+extern "C" void hs_set_row_cap(int cap) { g_row_cap = cap <= 4 ? 4 : 8; }
 
 template <int NB, class WT>
 static void init_env(const WT& W, Env<NB>& e) {
@@ -28,8 +42,9 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
                      int early_exit, float* traj, int* win_out, int* steps_out, int* overflow) {
     static Env<NB> e;
     init_env(W, e);
-    static f4 pool[4 * 64];
-    Stepper<NB, MAXC, WT, PR> sim(W, e, pool);
+    using Sim = Stepper<NB, MAXC, WT, PR>;
+    alignas(16) static unsigned char pool[Sim::kWarpBytes];
+    Sim sim(W, e, pool);
     float score = INFINITY;
     int win = -1, steps = 0;
     auto record = [&]() {
@@ -44,6 +59,7 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
     for (int g = 0; g < genome_len && !stop; ++g) {
         for (int r = 0; r < repeat_move; ++r) {
             float d = sim.step(genome[g] & 7u);
+            count_need(sim);
             ++steps;
             if (traj) sim.detect_pending();  // what a kernel does before it stores the state
             record();
@@ -55,6 +71,7 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
     }
     for (int r = 0; r < number_of_steps % repeat_move; ++r) {
         float d = sim.step(0u);
+        count_need(sim);
         ++steps;
         if (traj) sim.detect_pending();
         record();
@@ -103,18 +120,18 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
     if (rc != PRL_OK) return rc;
     const DevWorld& W = w.dev;
 #define HS_ARGS genome, genome_len, repeat_move, number_of_steps, early_exit, traj, win, steps, overflow
-    const bool small_pool = g_pool_rows < 64;
+    const bool small_pool = g_row_cap < 8;
     // the same variant choice as the library (prl_api.cu pick_variant): small worlds run with the
     // compact tables and slot == pair manifolds, the rest with the general tables
     if (world_fits<DevWorldSmall>(W) && W.n_bodies <= 2) {
         static DevWorldSmall S;
         copy_world(S, W);
-        if (W.n_bodies == 1) *score = small_pool ? rollout<1, 32>(S, HS_ARGS) : rollout<1, 64>(S, HS_ARGS);
-        else *score = small_pool ? rollout<2, 32>(S, HS_ARGS) : rollout<2, 64>(S, HS_ARGS);
+        if (W.n_bodies == 1) *score = small_pool ? rollout<1, 4>(S, HS_ARGS) : rollout<1, 8>(S, HS_ARGS);
+        else *score = small_pool ? rollout<2, 4>(S, HS_ARGS) : rollout<2, 8>(S, HS_ARGS);
     } else if (W.n_bodies == 1) {
-        *score = small_pool ? rollout<1, 32>(W, HS_ARGS) : rollout<1, 64>(W, HS_ARGS);
+        *score = small_pool ? rollout<1, 4>(W, HS_ARGS) : rollout<1, 8>(W, HS_ARGS);
     } else {
-        *score = small_pool ? rollout<MAXB, 32>(W, HS_ARGS) : rollout<MAXB, 64>(W, HS_ARGS);
+        *score = small_pool ? rollout<MAXB, 4>(W, HS_ARGS) : rollout<MAXB, 8>(W, HS_ARGS);
     }
 #undef HS_ARGS
     return 0;

@@ -60,18 +60,19 @@ def test_trajectories_bit_exact(name):
         assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
 
 
-def test_row_pool_size_does_not_change_results():
-    """The solver's constraint rows live in a shared-memory pool whose rows are XOR-swizzled;
-    the pool's size must not matter."""
+def test_row_storage_layout_does_not_change_results():
+    """The solver's constraint rows live in per-lane columns of shared-memory planes; with 4-row
+    columns an environment with more than 4 rows spills into the neighbouring columns (the kernels
+    then solve in rounds). The column height must not matter."""
     world = world_dict("push")
-    hostsim().hs_set_pool_rows(32)
+    hostsim().hs_set_row_cap(4)
     try:
         for g in random_genomes(3, 50, 12):
             t, _, _, _ = host_rollout(world, g, 20, 1000, False)
             o = oracle_traj(world, g, 20, 1000)
             assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
     finally:
-        hostsim().hs_set_pool_rows(64)
+        hostsim().hs_set_row_cap(8)
 
 
 @pytest.mark.parametrize("name", WORLDS)
