@@ -453,8 +453,9 @@ struct Stepper {
     // read with the widest conflict-free access, and a lane's rows sit in the lane's own COLUMN
     // (entry = row * 32 + lane), so that every access of a warp covers consecutive addresses:
     //   plane 0  f4  (dir.x, dir.y, gcross2, t_gcross2)                  both sweeps
-    //   plane 1  f4  (rhs, r, rhs_wo_bias, bits)                         normal sweeps
-    //                bits = body1 | body2 << 8 | fast << 16
+    //   plane 1  f4  (rhs, r, rhs_wo_bias, softness)                     normal sweeps
+    //                softness = the constraint's cfm_factor as a float (NB <= 2), or the bits
+    //                body1 | body2 << 8 | rigid << 16 (NB > 2)
     //   plane 2  f2  (t_rhs, t_r)                                        friction sweeps
     //   plane 3  f   accumulated normal impulse                          read + written
     //   plane 4  f   accumulated tangent impulse                         read + written
@@ -462,9 +463,11 @@ struct Stepper {
     // With at most one pushable block (NB <= 2) the only two-body rows are the <= 2 rows of the
     // player-block manifold, whose plane 5 stays in registers (tb_g1 / tb_tg1), and a ground
     // row's body follows from its position in the row list (player pairs sort first).
-    // A column holds CAP rows. An environment that needs more borrows the columns of its
-    // neighbours: the warp then solves in G rounds, lane l owning columns [l & ~(G-1), +G) in
-    // round l & (G-1) (see the kernels); G == 1 in all but a fraction of a percent of the steps.
+    // A column holds CAP rows. If an environment of the warp needs more, the warp solves in G
+    // rounds (G = 2, 4, 8; see the kernels): the 32 / G lanes of a round re-shape the planes into
+    // 32 / G columns of G * CAP rows. Either way row j of a lane is entry ent0 + j * stride with
+    // stride = 32 / G and ent0 = the lane's column, so the lanes of a round always touch
+    // consecutive entries. G == 1 in all but a fraction of a percent of the steps.
     static constexpr int kCap = CAP;
     static constexpr int kCapLog2 = CAP == 4 ? 2 : 3;
     static_assert(CAP == 4 || CAP == 8, "column height must be 4 or 8 rows");
@@ -478,7 +481,8 @@ struct Stepper {
     const WT& W;
     E& e;
     unsigned char* pool;    // the warp's planes
-    int col;                // first column of this lane, this step
+    int ent0, stride;       // entry of my row 0 and distance between my rows, this step
+    float cfm_reg;          // cfm_factor
     float tb_g1[2], tb_tg1[2];
     // constraint selection of the current step (begin_step -> finish_step)
     uint32_t active;
@@ -489,14 +493,16 @@ struct Stepper {
     uint32_t pend_moved;
     bool pend_all, first_step;
     PRL_D Stepper(const WT& w, E& env, void* warp_pool)
-        : W(w), e(env), pool(static_cast<unsigned char*>(warp_pool)), col(0), active(0), cons(0), ncons(0), need(0), ntb(0),
+        : W(w), e(env), pool(static_cast<unsigned char*>(warp_pool)), ent0(0), stride(1), cfm_reg(w.cfm_factor), active(0), cons(0), ncons(0), need(0), ntb(0),
           nplayer(0), pend_moved(0), pend_all((env.flags & FLAG_FRESH) != 0), first_step(false) {
         tb_g1[0] = tb_g1[1] = tb_tg1[0] = tb_tg1[1] = 0.0f;
 #pragma unroll
         for (int b = 0; b < NB; ++b) im_reg[b] = w.inv_mass[b];
     }
-    // entry of my row j: row j % CAP of column col + j / CAP
-    PRL_D int row_entry(int j) const { return ((j & (CAP - 1)) << 5) + col + (j >> kCapLog2); }
+    // The sweeps fetch one row ahead without a bounds check: the entry after a lane's last row may
+    // lie up to 32 entries past a plane (it is never used), so a block's planes are followed by kPoolPad bytes.
+    static constexpr int kPoolPad = 256;
+    PRL_D int row_entry(int j) const { return ent0 + j * stride; }
     PRL_D f4& q0(int en) const { return reinterpret_cast<f4*>(pool)[en]; }
     PRL_D f4& q1(int en) const { return reinterpret_cast<f4*>(pool + kOff1)[en]; }
     PRL_D f2& q2(int en) const { return reinterpret_cast<f2*>(pool + kOff2)[en]; }
@@ -813,7 +819,7 @@ struct Stepper {
             }
             v2 dv = (vel1 - vel2) + V(0.0f, 0.0f);
             r0.x = dir1.x; r0.y = dir1.y; r0.z = gcross2; r0.w = t_gcross2;
-            r1.x = rhs; r1.y = pm; r1.z = rhs_wo_bias; r1.w = bits_f32(bodies);
+            r1.x = rhs; r1.y = pm; r1.z = rhs_wo_bias; r1.w = NB <= 2 ? cfm_reg : bits_f32(bodies);
             f2 r2;
             r2.x = dot(dv, tan1); r2.y = inv0(tr);
             int j = nrows + k;
@@ -831,7 +837,7 @@ struct Stepper {
         }
         if (fast) {  // a fast contact makes the whole constraint rigid (cfm_factor 1)
 #pragma unroll 1
-            for (int k = 0; k < ns; ++k) q1(row_entry(nrows + k)).w = bits_f32(bodies | (1u << 16));
+            for (int k = 0; k < ns; ++k) q1(row_entry(nrows + k)).w = NB <= 2 ? 1.0f : bits_f32(bodies | (1u << 16));
         }
         return nrows + ns;
     }
@@ -851,35 +857,36 @@ struct Stepper {
         r.a = q0(en); r.c = q2(en); r.acc = acc_t(en); r.accn = acc_n(en);
         r.bits = BODY < 0 ? f32_bits(q1(en).w) : 0u;
     }
+    // softness of a row: rapier's cfm_factor, 1 for a constraint with a fast contact and for every
+    // constraint once the bias has been removed (remove_bias)
+    PRL_D float row_cfm(float w) const { return NB <= 2 ? w : ((f32_bits(w) >> 16) ? 1.0f : cfm_reg); }
     template <int BODY>
-    PRL_D void ground_row_n(int en, bool biased, const RowN& r, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+    PRL_D void ground_row_n(int en, const RowN& r, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+        constexpr int B = BODY >= 0 ? BODY : 0;
         const v2 dir = V(r.a.x, r.a.y);
-        const float g2 = r.a.z, rr = r.b.y, acc = r.acc;
-        const float rhs = biased ? r.b.x : r.b.z;
-        const uint32_t bits = f32_bits(r.b.w);
-        const int b2 = BODY >= 0 ? BODY : (int)((bits >> 8) & 0xffu);
-        const float im2 = BODY >= 0 ? im_reg[BODY >= 0 ? BODY : 0] : sel(im_reg, b2);
-        v2 l2 = BODY >= 0 ? V(dlx[BODY >= 0 ? BODY : 0], dly[BODY >= 0 ? BODY : 0]) : V(sel(dlx, b2), sel(dly, b2));
-        float a2 = BODY >= 0 ? da[BODY >= 0 ? BODY : 0] : sel(da, b2);
+        const float g2 = r.a.z, rr = r.b.y, acc = r.acc, rhs = r.b.x;
+        const int b2 = BODY >= 0 ? BODY : (int)((f32_bits(r.b.w) >> 8) & 0xffu);
+        const float im2 = BODY >= 0 ? im_reg[B] : sel(im_reg, b2);
+        v2 l2 = BODY >= 0 ? V(dlx[B], dly[B]) : V(sel(dlx, b2), sel(dly, b2));
+        float a2 = BODY >= 0 ? da[B] : sel(da, b2);
         float dvel = -dot(dir, l2) + g2 * a2 + rhs;
-        // the stabilisation sweep runs without the penetration bias and without softness
-        float cfm = (biased && !(bits >> 16)) ? W.cfm_factor : 1.0f;
-        float ni = cfm * fmaxf(acc - rr * dvel, 0.0f);
+        float ni = row_cfm(r.b.w) * fmaxf(acc - rr * dvel, 0.0f);
         acc_n(en) = ni;
         float dl = ni - acc;
         l2 = l2 + (dir * im2) * -dl;
         a2 += g2 * dl;
-        if (BODY >= 0) { dlx[BODY >= 0 ? BODY : 0] = l2.x; dly[BODY >= 0 ? BODY : 0] = l2.y; da[BODY >= 0 ? BODY : 0] = a2; }
+        if (BODY >= 0) { dlx[B] = l2.x; dly[B] = l2.y; da[B] = a2; }
         else { put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2); }
     }
     template <int BODY>
     PRL_D void ground_row_t(int en, const RowT& r, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+        constexpr int B = BODY >= 0 ? BODY : 0;
         const v2 dir = V(-r.a.y, r.a.x);  // tangent
         const float g2 = r.a.w, rhs = r.c.x, rr = r.c.y, acc = r.acc;
         const int b2 = BODY >= 0 ? BODY : (int)((r.bits >> 8) & 0xffu);
-        const float im2 = BODY >= 0 ? im_reg[BODY >= 0 ? BODY : 0] : sel(im_reg, b2);
-        v2 l2 = BODY >= 0 ? V(dlx[BODY >= 0 ? BODY : 0], dly[BODY >= 0 ? BODY : 0]) : V(sel(dlx, b2), sel(dly, b2));
-        float a2 = BODY >= 0 ? da[BODY >= 0 ? BODY : 0] : sel(da, b2);
+        const float im2 = BODY >= 0 ? im_reg[B] : sel(im_reg, b2);
+        v2 l2 = BODY >= 0 ? V(dlx[B], dly[B]) : V(sel(dlx, b2), sel(dly, b2));
+        float a2 = BODY >= 0 ? da[B] : sel(da, b2);
         float dvel = -dot(dir, l2) + g2 * a2 + rhs;
         float limit = kFriction * r.accn;
         float ni = fminf(fmaxf(acc - rr * dvel, -limit), limit);
@@ -887,48 +894,58 @@ struct Stepper {
         float dl = ni - acc;
         l2 = l2 + (dir * im2) * -dl;
         a2 += g2 * dl;
-        if (BODY >= 0) { dlx[BODY >= 0 ? BODY : 0] = l2.x; dly[BODY >= 0 ? BODY : 0] = l2.y; da[BODY >= 0 ? BODY : 0] = a2; }
+        if (BODY >= 0) { dlx[B] = l2.x; dly[B] = l2.y; da[B] = a2; }
         else { put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2); }
     }
+    // one sweep over my rows [jbegin, jend): two rows per trip, each fetched while the previous one
+    // is computed, in two alternating register sets
     template <bool NORMAL, int BODY>
-    PRL_D void ground_rows(int jbegin, int jend, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+    PRL_D void ground_rows(int jbegin, int jend, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
         if (jbegin >= jend) return;
         int en = row_entry(jbegin);
+        int left = jend - jbegin;
         if (NORMAL) {
-            RowN nx;
-            fetch(en, nx);
+            RowN ra, rb;
+            fetch(en, ra);
 #pragma unroll 1
-            for (int j = jbegin; j < jend; ++j) {
-                const RowN cur = nx;
-                const int cen = en;
-                en = row_entry(j + 1 < jend ? j + 1 : j);  // the last iteration re-reads its own row: no branch
-                fetch(en, nx);
-                ground_row_n<BODY>(cen, biased, cur, dlx, dly, da);
+            while (true) {
+                const int en1 = en + stride;
+                fetch(en1, rb);
+                ground_row_n<BODY>(en, ra, dlx, dly, da);
+                if (--left == 0) break;
+                en = en1 + stride;
+                fetch(en, ra);
+                ground_row_n<BODY>(en1, rb, dlx, dly, da);
+                if (--left == 0) break;
             }
         } else {
-            RowT nx;
-            fetch<BODY>(en, nx);
+            RowT ra, rb;
+            fetch<BODY>(en, ra);
 #pragma unroll 1
-            for (int j = jbegin; j < jend; ++j) {
-                const RowT cur = nx;
-                const int cen = en;
-                en = row_entry(j + 1 < jend ? j + 1 : j);
-                fetch<BODY>(en, nx);
-                ground_row_t<BODY>(cen, cur, dlx, dly, da);
+            while (true) {
+                const int en1 = en + stride;
+                fetch<BODY>(en1, rb);
+                ground_row_t<BODY>(en, ra, dlx, dly, da);
+                if (--left == 0) break;
+                en = en1 + stride;
+                fetch<BODY>(en, ra);
+                ground_row_t<BODY>(en1, rb, dlx, dly, da);
+                if (--left == 0) break;
             }
         }
     }
     template <bool NORMAL>
-    PRL_D void two_body_row(int j, bool biased, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
+    PRL_D void two_body_row(int j, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
         const int en = row_entry(j);
         const f4 r0 = q0(en);
         v2 dir = V(r0.x, r0.y);
         uint32_t bodies = 0;
-        float g1, g2, rhs, rr, acc, accn = 0.0f;
+        float g1, g2, rhs, rr, acc, accn = 0.0f, cfm = 1.0f;
         if (NORMAL) {
             const f4 r1 = q1(en);
-            bodies = f32_bits(r1.w);
-            g2 = r0.z; rr = r1.y; rhs = biased ? r1.x : r1.z; acc = acc_n(en);
+            if (NB > 2) bodies = f32_bits(r1.w);
+            cfm = row_cfm(r1.w);
+            g2 = r0.z; rr = r1.y; rhs = r1.x; acc = acc_n(en);
         } else {
             const f2 r2 = q2(en);
             if (NB > 2) bodies = f32_bits(q1(en).w);
@@ -943,7 +960,6 @@ struct Stepper {
         float dvel = dot(dir, l1) + g1 * a1 - dot(dir, l2) + g2 * a2 + rhs;
         float ni;
         if (NORMAL) {
-            float cfm = (biased && !(bodies >> 16)) ? W.cfm_factor : 1.0f;
             ni = cfm * fmaxf(acc - rr * dvel, 0.0f);
             acc_n(en) = ni;
         } else {
@@ -958,6 +974,18 @@ struct Stepper {
         a2 += g2 * dl;
         put(dlx, b1, l1.x); put(dly, b1, l1.y); put(da, b1, a1);
         put(dlx, b2, l2.x); put(dly, b2, l2.y); put(da, b2, a2);
+    }
+    // rapier's remove_bias before the stabilisation sweep: every row continues without the
+    // penetration bias (rhs := rhs_wo_bias) and without softness (cfm_factor := 1)
+    PRL_D void remove_bias(int nrows) {
+        int en = row_entry(0);
+#pragma unroll 1
+        for (int j = 0; j < nrows; ++j, en += stride) {
+            f4 r = q1(en);
+            r.x = r.z;
+            r.w = NB <= 2 ? 1.0f : bits_f32(f32_bits(r.w) | (1u << 16));
+            q1(en) = r;
+        }
     }
 
     // rapier IslandManager::update_active_set_with_contacts + NarrowPhase::select_active_contacts:
@@ -995,10 +1023,11 @@ struct Stepper {
     }
 
     // constraint build + VelocitySolver::solve + position update for the active bodies (SURVEY
-    // A.3 stages 4-7), with this lane's rows in the warp's columns [first_col, ...). Returns the
-    // mask of bodies that moved.
-    PRL_D uint32_t solve_and_integrate(int first_col) {
-        col = first_col;
+    // A.3 stages 4-7), with this lane's rows at entries first_entry + j * entry_stride of the
+    // warp's planes. Returns the mask of bodies that moved.
+    PRL_D uint32_t solve_and_integrate(int first_entry, int entry_stride) {
+        ent0 = first_entry;
+        stride = entry_stride;
         int nrows = 0;
 #pragma unroll 1
         for (int i = 0; i < ncons; ++i) nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows);
@@ -1027,30 +1056,30 @@ struct Stepper {
                         nx[b] = np.t.x; ny[b] = np.t.y; nc[b] = np.c; ns[b] = np.s;
                     }
                 }
+                remove_bias(nrows);
             }
-            const bool biased = sweep < 12;
             // ground rows: rows [ntb, jsplit) belong to the player's pairs, [jsplit, nrows) to block pairs
             const int jsplit = ntb + nplayer;
             if (sweep == 12 || (sweep < 8 && (sweep & 1) == 0)) {
                 if (NB > 1) {
 #pragma unroll 1
-                    for (int j = 0; j < ntb; ++j) two_body_row<true>(j, biased, dlx, dly, da);
+                    for (int j = 0; j < ntb; ++j) two_body_row<true>(j, dlx, dly, da);
                 }
-                if (NB == 1) ground_rows<true, 0>(0, nrows, biased, dlx, dly, da);
+                if (NB == 1) ground_rows<true, 0>(0, nrows, dlx, dly, da);
                 else if (NB == 2) {
-                    ground_rows<true, 0>(ntb, jsplit, biased, dlx, dly, da);
-                    ground_rows<true, 1>(jsplit, nrows, biased, dlx, dly, da);
-                } else ground_rows<true, -1>(ntb, nrows, biased, dlx, dly, da);
+                    ground_rows<true, 0>(ntb, jsplit, dlx, dly, da);
+                    ground_rows<true, 1>(jsplit, nrows, dlx, dly, da);
+                } else ground_rows<true, -1>(ntb, nrows, dlx, dly, da);
             } else {
                 if (NB > 1) {
 #pragma unroll 1
-                    for (int j = 0; j < ntb; ++j) two_body_row<false>(j, biased, dlx, dly, da);
+                    for (int j = 0; j < ntb; ++j) two_body_row<false>(j, dlx, dly, da);
                 }
-                if (NB == 1) ground_rows<false, 0>(0, nrows, biased, dlx, dly, da);
+                if (NB == 1) ground_rows<false, 0>(0, nrows, dlx, dly, da);
                 else if (NB == 2) {
-                    ground_rows<false, 0>(ntb, jsplit, biased, dlx, dly, da);
-                    ground_rows<false, 1>(jsplit, nrows, biased, dlx, dly, da);
-                } else ground_rows<false, -1>(ntb, nrows, biased, dlx, dly, da);
+                    ground_rows<false, 0>(ntb, jsplit, dlx, dly, da);
+                    ground_rows<false, 1>(jsplit, nrows, dlx, dly, da);
+                } else ground_rows<false, -1>(ntb, nrows, dlx, dly, da);
             }
         }
 #pragma unroll
@@ -1275,7 +1304,7 @@ struct Stepper {
     //   detect_pending();                 // broad + narrow phase owed by the previous position update
     //   need = begin_step(move);          // ground scan + move impulses + constraint selection
     //   (kernel) the warp agrees on how many columns of row storage a lane gets this step
-    //   d = finish_step(first column);    // solve, integrate, win latch
+    //   d = finish_step(entry, stride);   // solve, integrate, win latch
     //
     // rapier runs the detection at the END of PhysicsPipeline::step; running it at the start of
     // the next step (and once more after the last one) is the same sequence of operations.
@@ -1297,8 +1326,8 @@ struct Stepper {
         select_constraints();
         return need;
     }
-    PRL_D float finish_step(int first_col) {
-        pend_moved = solve_and_integrate(first_col);
+    PRL_D float finish_step(int first_entry, int entry_stride) {
+        pend_moved = solve_and_integrate(first_entry, entry_stride);
         // query_pipeline.update (common.rs:330-331) is never queried: omitted
         float d = distance_to_goals();
         if (!(e.flags & FLAG_WON) && W.n_goals > 0 && d < 1e-7f) e.flags |= FLAG_WON;
@@ -1309,7 +1338,7 @@ struct Stepper {
     PRL_D float step(uint32_t mv) {
         detect_pending();
         begin_step(mv);
-        return finish_step(0);  // a single lane owns every column
+        return finish_step(0, 1);  // a single lane owns the planes
     }
 };
 

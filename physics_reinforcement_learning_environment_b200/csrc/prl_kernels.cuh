@@ -38,26 +38,28 @@ constexpr int kRegroupKeys = 34;  // 0 = finished, 1 + min(rows, 32)
 constexpr size_t kRegroupBytes = (kRegroupKeys + 2 * kBigBlock) * sizeof(int);
 template <int NB, class WT>
 constexpr size_t rollout_smem_bytes(int block) {
-    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * SimOf<NB, WT>::kWarpBytes + (block == kBigBlock ? kRegroupBytes : 0);
+    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * SimOf<NB, WT>::kWarpBytes + SimOf<NB, WT>::kPoolPad +
+           (block == kBigBlock ? kRegroupBytes : 0);
 }
 
-// One step's solve for the lanes of a warp. The warp first agrees on how many columns of row
-// storage a lane gets: G = 1 unless some environment needs more rows than a column holds, in
-// which case lanes take turns in G rounds, lane l using the G columns of its group in round
-// l % G. `body(first_col)` runs finish_step and the caller's bookkeeping. Every lane of the warp
-// must call this (lanes with nothing to do pass run = false, need = 0).
+// One step's solve for the lanes of a warp. The warp first agrees on the shape of its row
+// storage: 32 columns of kCap rows unless some environment needs more, in which case the lanes
+// take turns in G rounds and the 32 / G lanes of a round use 32 / G columns of G * kCap rows
+// (prl_device.cuh, Stepper). `body(entry, stride)` runs finish_step and the caller's bookkeeping.
+// Every lane of the warp must call this (lanes with nothing to do pass run = false, need = 0).
 template <class SIM, class F>
 __device__ __forceinline__ void solve_in_rounds(bool run, int need, F&& body) {
     const int mx = warp_max(need);
     const int lane = (int)(threadIdx.x & 31u);
     if (mx <= SIM::kCap) {
-        if (run) body(lane);
+        if (run) body(lane, 32);
         return;
     }
-    const int G = mx <= 2 * SIM::kCap ? 2 : (mx <= 4 * SIM::kCap ? 4 : 8);
+    const int lg = mx <= 2 * SIM::kCap ? 1 : (mx <= 4 * SIM::kCap ? 2 : 3);
+    __syncwarp();  // the rounds overwrite other lanes' columns of the previous step
 #pragma unroll 1
-    for (int r = 0; r < G; ++r) {
-        if (run && (lane & (G - 1)) == r) body(lane & ~(G - 1));
+    for (int r = 0; r < (1 << lg); ++r) {
+        if (run && (lane & ((1 << lg) - 1)) == r) body(lane >> lg, 32 >> lg);
         __syncwarp();
     }
 }
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) step_kernel(const DevW
                                                       int* __restrict__ overflow) {
     using Sim = SimOf<NB, WT>;
     __shared__ WT W;
-    __shared__ __align__(16) unsigned char row_pool[(kBlock / 32) * Sim::kWarpBytes];
+    __shared__ __align__(16) unsigned char row_pool[(kBlock / 32) * Sim::kWarpBytes + Sim::kPoolPad];
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     // the warp agrees on its row storage with a warp vote every step, so every lane stays alive:
@@ -234,8 +236,8 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) step_kernel(const DevW
         sim.detect_pending();
         if (t == n_steps) break;
         const int need = sim.begin_step(mv);
-        solve_in_rounds<Sim>(true, need, [&](int first_col) {
-            float d = sim.finish_step(first_col);
+        solve_in_rounds<Sim>(true, need, [&](int entry, int stride) {
+            float d = sim.finish_step(entry, stride);
             ++steps;
             score = fminf(score, d);
             if ((e.flags & FLAG_WON) && win_step < 0) win_step = steps;
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     const int total = main_steps + number_of_steps % repeat_move;
     int g = 0, rep = 0, t = 0, iter = 0;
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
-    int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes);  // only if BLOCK == kBigBlock
+    int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes + Sim::kPoolPad);  // only if BLOCK == kBigBlock
 #pragma unroll 1
     while (true) {
         sim.detect_pending();
@@ -328,8 +330,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
         const bool run = t < total;
         const bool in_genes = t < main_steps;
         const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
-        solve_in_rounds<Sim>(run, need, [&](int first_col) {
-            float d = sim.finish_step(first_col);
+        solve_in_rounds<Sim>(run, need, [&](int entry, int stride) {
+            float d = sim.finish_step(entry, stride);
             ++steps;
             ++t;
             score = fminf(score, d);

@@ -43,7 +43,7 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
     static Env<NB> e;
     init_env(W, e);
     using Sim = Stepper<NB, MAXC, WT, PR>;
-    alignas(16) static unsigned char pool[Sim::kWarpBytes];
+    alignas(16) static unsigned char pool[Sim::kWarpBytes + Sim::kPoolPad];
     Sim sim(W, e, pool);
     float score = INFINITY;
     int win = -1, steps = 0;
