@@ -36,6 +36,14 @@
 #define PRL_COLD static inline
 #endif
 
+// PRL_PHASE_TIMING (profiling builds only, never the product): per-warp cycle counts of the phases
+// of a step, printed by block 0 of the rollout kernel
+#if defined(PRL_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define PRL_TICK(i) do { long long c_ = clock64(); tacc[i] += c_ - tlast; tlast = c_; } while (0)
+#else
+#define PRL_TICK(i) do { } while (0)
+#endif
+
 namespace prl {
 
 PRL_D int first_zero_bit(uint32_t used) {  // index of the lowest clear bit, 32 if none
@@ -430,6 +438,14 @@ struct Env {
     uint32_t used;       // bit s = slot s is live
     uint64_t spair[2];   // byte s = pair index of slot s (registers: the lists are walked every stage)
     uint32_t sns;        // 2 bits per slot: number of solver contacts of slot s
+};
+
+// The contact records of one environment, indexed at run time and therefore in thread-local
+// memory (16-byte rows, so one record moves with one LDL.128 / STL.128). They are a separate
+// object from Env on purpose: a struct that is indexed with a run-time subscript anywhere is
+// kept in memory as a whole by the compiler, and the body state must stay in registers.
+template <int S = MAXC>
+struct Contacts {
     // mf[s]: the cached contact manifold of one collider pair
     //   [0] = (hdr, n1.x, n1.y, n2.x)      hdr bits = pair | npts << 8 | n_solver_contacts << 12
     //   [1] = (n2.y, p1a.x, p1a.y, p2a.x)
@@ -469,8 +485,7 @@ struct Stepper {
     // stride = 32 / G and ent0 = the lane's column, so the lanes of a round always touch
     // consecutive entries. G == 1 in all but a fraction of a percent of the steps.
     static constexpr int kCap = CAP;
-    static constexpr int kCapLog2 = CAP == 4 ? 2 : 3;
-    static_assert(CAP == 4 || CAP == 8, "column height must be 4 or 8 rows");
+    static_assert(CAP >= 4 && CAP <= 8, "column height");
     static constexpr int kEntries = 32 * CAP;   // entries per plane per warp
     static constexpr int kRowBytes = 48 + (NB > 2 ? 8 : 0);
     static constexpr int kWarpBytes = kEntries * kRowBytes;
@@ -480,6 +495,7 @@ struct Stepper {
     static_assert(kMaxRows <= 8 * CAP, "eight columns must hold every row of one environment");
     const WT& W;
     E& e;
+    Contacts<S>& k;
     unsigned char* pool;    // the warp's planes
     int ent0, stride;       // entry of my row 0 and distance between my rows, this step
     float cfm_reg;          // cfm_factor
@@ -492,9 +508,22 @@ struct Stepper {
     // collision detection owed for the poses of the last position update (detect_pending)
     uint32_t pend_moved;
     bool pend_all, first_step;
-    PRL_D Stepper(const WT& w, E& env, void* warp_pool)
-        : W(w), e(env), pool(static_cast<unsigned char*>(warp_pool)), ent0(0), stride(1), cfm_reg(w.cfm_factor), active(0), cons(0), ncons(0), need(0), ntb(0),
-          nplayer(0), pend_moved(0), pend_all((env.flags & FLAG_FRESH) != 0), first_step(false) {
+    // Ground-contact scan (common.rs:216-244) gathered while the narrow phase has the player's
+    // solver contacts in registers: the first two floor contacts in the reference's iteration
+    // order (pair order, then point order). gs_n = their number (more than two: count only), or -1
+    // if the narrow phase did not visit the player's pairs since the last scan (player asleep,
+    // state just loaded): player_move then reads the stored solver contacts instead.
+    int gs_n;
+    float gs_x[2], gs_y[2];
+    int gs_b[2];
+#if defined(PRL_PHASE_TIMING)
+    long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#endif
+    PRL_D Stepper(const WT& w, E& env, Contacts<S>& contacts, void* warp_pool)
+        : W(w), e(env), k(contacts), pool(static_cast<unsigned char*>(warp_pool)), ent0(0), stride(1), cfm_reg(w.cfm_factor), active(0), cons(0), ncons(0), need(0), ntb(0),
+          nplayer(0), pend_moved(0), pend_all((env.flags & FLAG_FRESH) != 0), first_step(false), gs_n(-1) {
+        gs_x[0] = gs_x[1] = gs_y[0] = gs_y[1] = 0.0f;
+        gs_b[0] = gs_b[1] = -1;
         tb_g1[0] = tb_g1[1] = tb_tg1[0] = tb_tg1[1] = 0.0f;
 #pragma unroll
         for (int b = 0; b < NB; ++b) im_reg[b] = w.inv_mass[b];
@@ -540,7 +569,7 @@ struct Stepper {
     PRL_D void wake_strong(int b) { e.sleeping &= ~(1u << b); put(e.timer, b, 0.0f); }
 
     PRL_D void load_manifold(int slot, Manifold& m) const {
-        f4 a = e.mf[slot][0], b = e.mf[slot][1], c = e.mf[slot][2], d = e.mf[slot][3];
+        f4 a = k.mf[slot][0], b = k.mf[slot][1], c = k.mf[slot][2], d = k.mf[slot][3];
         m.npts = (int)((f32_bits(a.x) >> 8) & 0xfu);
         m.n1 = V(a.y, a.z); m.n2 = V(a.w, b.x);
         m.p1[0] = V(b.y, b.z); m.p2[0] = V(b.w, c.x); m.dist[0] = c.y;
@@ -549,6 +578,7 @@ struct Stepper {
     // store a manifold with points and refresh its solver contacts (rapier
     // NarrowPhase::compute_contacts tail: points with dist < prediction, at the midpoint between
     // the two surfaces, in world space)
+    template <bool SCAN = false>
     PRL_D void store_manifold(int slot, int pair, const Manifold& m, const Iso& pose1) {
         v2 normal = rot(pose1.c, pose1.s, m.n1);
         int ns = 0;
@@ -564,6 +594,20 @@ struct Stepper {
                 ++ns;
             }
         }
+        if (SCAN && gs_n >= 0) {  // a player pair: floor contacts among its solver contacts (common.rs:234-238)
+            const int body = W.body_of[W.pair_c2[pair]];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k < ns) {
+                    float qy = (py[k] - (e.y[0] - W.lower_off)) / W.radius;
+                    if (qy < -0.707f) {
+                        if (gs_n == 0) { gs_x[0] = px[k]; gs_y[0] = py[k]; gs_b[0] = body; }
+                        else if (gs_n == 1) { gs_x[1] = px[k]; gs_y[1] = py[k]; gs_b[1] = body; }
+                        ++gs_n;
+                    }
+                }
+            }
+        }
         f4 a, b, c, d;
         a.x = bits_f32((uint32_t)pair | ((uint32_t)m.npts << 8));
         e.sns = (e.sns & ~(3u << (2 * slot))) | ((uint32_t)ns << (2 * slot));
@@ -576,21 +620,22 @@ struct Stepper {
         b.x = m.n2.y; b.y = m.p1[0].x; b.z = m.p1[0].y; b.w = m.p2[0].x;
         c.x = m.p2[0].y; c.y = m.dist[0]; c.z = m.p1[1].x; c.w = m.p1[1].y;
         d.x = m.p2[1].x; d.y = m.p2[1].y; d.z = m.dist[1]; d.w = 0.0f;
-        e.mf[slot][0] = a; e.mf[slot][1] = b; e.mf[slot][2] = c; e.mf[slot][3] = d;
+        k.mf[slot][0] = a; k.mf[slot][1] = b; k.mf[slot][2] = c; k.mf[slot][3] = d;
         f4 s0, s1;
         s0.x = normal.x; s0.y = normal.y; s0.z = px[0]; s0.w = py[0];
         s1.x = pd[0]; s1.y = px[1]; s1.z = py[1]; s1.w = pd[1];
-        e.sc[slot][0] = s0; e.sc[slot][1] = s1;
+        k.sc[slot][0] = s0; k.sc[slot][1] = s1;
     }
     // after a load from HBM: solver contacts are a pure function of the manifold and collider 1's
     // pose, so they are not part of the stored state
     PRL_D void refresh_solver_contacts() {
+        gs_n = -1;
 #pragma unroll 1
         for (int it = it_begin(); it_ok(it); it = it_next(it)) {
             int slot = it_slot(it);
             Manifold m;
             load_manifold(slot, m);
-            int p = (int)(f32_bits(e.mf[slot][0].x) & 0xffu);
+            int p = (int)(f32_bits(k.mf[slot][0].x) & 0xffu);
             store_manifold(slot, p, m, collider_pose(W.pair_c1[p]));
         }
     }
@@ -635,8 +680,51 @@ struct Stepper {
     }
 
     // common.rs:216-313: ground-contact scan over the player's contact pairs, then the move
-    // impulses. The player's pairs are the head of the sorted manifold list.
+    // impulses. The scan normally comes from the narrow phase (gs_*, see store_manifold).
     PRL_D void player_move(uint32_t mv) {
+        if (gs_n < 0 || gs_n > 2) { player_move_stored(mv); return; }
+        const int nfc = gs_n;
+        if (nfc == 0) return;
+        v2 lower = V(e.x[0], e.y[0] - W.lower_off);
+        // min_by keeps the first minimum, max_by the last maximum (common.rs:249-254, 273-278)
+        const bool second_min = nfc == 2 && gs_x[1] < gs_x[0];
+        const bool second_max = nfc == 2 && !(gs_x[1] < gs_x[0]);
+        v2 player_impulse = V(0.0f, 0.0f);
+        // left / right: tangent impulse at the extreme floor contact (common.rs:249-295)
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            if (mv & (1u << side)) {
+                const bool second = side == 0 ? second_min : second_max;
+                v2 pt = second ? V(gs_x[1], gs_y[1]) : V(gs_x[0], gs_y[0]);
+                int body = second ? gs_b[1] : gs_b[0];
+                v2 n = pt - lower;
+                float len = sqrtf(n.x * n.x + n.y * n.y);
+                n = V(n.x / len, n.y / len);
+                v2 imp = side == 0 ? V(0.003f * n.y, -0.003f * n.x) : V(-0.003f * n.y, 0.003f * n.x);
+                if (NB > 1 && body >= 0) apply_impulse_at_point(body, -imp, pt);
+                player_impulse = player_impulse + imp;
+            }
+        }
+        if (mv & 4u) {  // up: the jump impulse is shared by all floor contacts (common.rs:297-310)
+            float cnt = (float)nfc;
+#pragma unroll 1
+            for (int k = 0; k < nfc; ++k) {
+                v2 pt = k == 0 ? V(gs_x[0], gs_y[0]) : V(gs_x[1], gs_y[1]);
+                int body = k == 0 ? gs_b[0] : gs_b[1];
+                v2 n = pt - lower;
+                float len = sqrtf(n.x * n.x + n.y * n.y);
+                n = V(n.x / len, n.y / len);
+                v2 imp = V(-0.1f * n.x / cnt, -0.1f * n.y / cnt);
+                if (NB > 1 && body >= 0) apply_impulse_at_point(body, -imp, pt);
+                player_impulse = player_impulse + imp;
+            }
+        }
+        apply_impulse(0, player_impulse);
+    }
+    // The same from the stored solver contacts (the narrow phase did not visit the player's pairs
+    // since the last scan, or there are more than two floor contacts). The player's pairs are the
+    // head of the sorted manifold list.
+    PRL_D void player_move_stored(uint32_t mv) {
         v2 lower = V(e.x[0], e.y[0] - W.lower_off);
         int nfc = 0;
         v2 pmin = V(0.0f, 0.0f), pmax = V(0.0f, 0.0f);
@@ -647,7 +735,7 @@ struct Stepper {
             int p = pair_of(slot), ns = ns_of(slot);
             if (p >= W.n_player_pairs) break;
             int body = W.body_of[W.pair_c2[p]];
-            f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
+            f4 s0 = k.sc[slot][0], s1 = k.sc[slot][1];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 if (i < ns) {
@@ -686,7 +774,7 @@ struct Stepper {
                 int ns = ns_of(slot);
                 if (pair_of(slot) >= W.n_player_pairs) break;
                 int body = W.body_of[W.pair_c2[pair_of(slot)]];
-                f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
+                f4 s0 = k.sc[slot][0], s1 = k.sc[slot][1];
 #pragma unroll 1
                 for (int i = 0; i < ns; ++i) {
                     v2 pt = i == 0 ? V(s0.z, s0.w) : V(s1.y, s1.z);
@@ -761,7 +849,7 @@ struct Stepper {
         int p = pair_of(slot), ns = ns_of(slot);
         int h1 = W.body_of[W.pair_c1[p]], h2 = W.body_of[W.pair_c2[p]];
         bool two_body = h1 >= 0 && h2 >= 0;
-        f4 s0 = e.sc[slot][0], s1 = e.sc[slot][1];
+        f4 s0 = k.sc[slot][0], s1 = k.sc[slot][1];
         v2 normal = V(s0.x, s0.y);
         v2 dir1;
         if (two_body) dir1 = -normal;
@@ -1031,6 +1119,7 @@ struct Stepper {
         int nrows = 0;
 #pragma unroll 1
         for (int i = 0; i < ncons; ++i) nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows);
+        PRL_TICK(5);
         float dlx[NB], dly[NB], da[NB];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -1082,6 +1171,7 @@ struct Stepper {
                 } else ground_rows<false, -1>(ntb, nrows, dlx, dly, da);
             }
         }
+        PRL_TICK(6);
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
             if ((active >> b) & 1u) {
@@ -1117,6 +1207,8 @@ struct Stepper {
     // overlapping pairs. A brute-force AABB test over the world's candidate pairs is
     // result-equivalent to rapier's sweep-and-prune.
     PRL_D void detect_collisions(uint32_t moved, bool all) {
+        // every live manifold of the player is revisited iff the player moved
+        gs_n = (all || (moved & 1u)) ? 0 : -1;
         float bmnx[NB], bmny[NB], bmxx[NB], bmxy[NB];
         {
             // player capsule: segment endpoints +- radius
@@ -1161,6 +1253,7 @@ struct Stepper {
                 }
                 if (modified && ov) cand |= bit;
             }
+            PRL_TICK(0);
             // narrow phase on "my i-th candidate": player pairs (capsule-cuboid) first, then block pairs
             const uint32_t pmask = (1u << W.n_player_pairs) - 1u;
 #pragma unroll 1
@@ -1173,8 +1266,9 @@ struct Stepper {
                 Iso pose1 = body_pose(0);
                 Iso pos12 = inv_mul(pose1, collider_pose(c2));
                 contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(W.hx[c2], W.hy[c2]), W.prediction);
-                commit_direct(p, m, pose1);
+                commit_direct<true>(p, m, pose1);
             }
+            PRL_TICK(1);
             if (NB > 1) {
 #pragma unroll 1
                 for (uint32_t m_ = cand & ~pmask; m_ != 0; m_ &= m_ - 1) {
@@ -1189,6 +1283,7 @@ struct Stepper {
                     commit_direct(p, m, pose1);
                 }
             }
+            PRL_TICK(2);
             return;
         }
         // Broad phase over the world's candidate pairs (ascending), merged with the sorted manifold
@@ -1242,7 +1337,7 @@ struct Stepper {
             Iso pose1 = body_pose(0);
             Iso pos12 = inv_mul(pose1, collider_pose(c2));
             contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(W.hx[c2], W.hy[c2]), W.prediction);
-            k = commit(p, k, have, slot, m, pose1);
+            k = commit<true>(p, k, have, slot, m, pose1);
         }
         if (NB > 1) {
 #pragma unroll 1
@@ -1262,10 +1357,11 @@ struct Stepper {
             }
         }
     }
+    template <bool SCAN = false>
     PRL_D void commit_direct(int p, const Manifold& m, const Iso& pose1) {
         if (m.npts > 0) {
             e.used |= 1u << p;
-            store_manifold(p, p, m, pose1);
+            store_manifold<SCAN>(p, p, m, pose1);
         } else {
             e.used &= ~(1u << p);
             e.sns &= ~(3u << (2 * p));
@@ -1273,10 +1369,11 @@ struct Stepper {
     }
     // write a narrow-phase result back at sorted position k; returns the position after it. Only
     // manifolds with points are kept: an empty one carries no state the next step can observe.
+    template <bool SCAN = false>
     PRL_D int commit(int p, int k, bool have, int slot, const Manifold& m, const Iso& pose1) {
         if (m.npts > 0) {
             if (!have) slot = insert_at(k);
-            if (slot >= 0) { store_manifold(slot, p, m, pose1); return k + 1; }
+            if (slot >= 0) { store_manifold<SCAN>(slot, p, m, pose1); return k + 1; }
             return k;
         }
         if (have) remove_at(k);
@@ -1323,7 +1420,9 @@ struct Stepper {
     PRL_D int begin_step(uint32_t mv) {
         if (!first_step) player_move(mv);
         first_step = false;
+        PRL_TICK(3);
         select_constraints();
+        PRL_TICK(4);
         return need;
     }
     PRL_D float finish_step(int first_entry, int entry_stride) {
@@ -1331,6 +1430,7 @@ struct Stepper {
         // query_pipeline.update (common.rs:330-331) is never queried: omitted
         float d = distance_to_goals();
         if (!(e.flags & FLAG_WON) && W.n_goals > 0 && d < 1e-7f) e.flags |= FLAG_WON;
+        PRL_TICK(7);
         return d;
     }
     // the whole step for one lane on its own (host build); call detect_pending() once more after

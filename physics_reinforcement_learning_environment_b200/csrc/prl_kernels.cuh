@@ -12,15 +12,27 @@
 #pragma once
 #include "prl_device.cuh"
 
+#if defined(PRL_PHASE_TIMING)
+#include <stdio.h>
+#define PRL_TICK_K(i) do { long long c_ = clock64(); sim.tacc[i] += c_ - sim.tlast; sim.tlast = c_; } while (0)
+#else
+#define PRL_TICK_K(i) do { } while (0)
+#endif
+
 namespace prl {
 
 constexpr int kBlock = 64;
 // Shared memory of a block: the world tables plus, per warp, the planes of velocity-constraint
-// rows (prl_device.cuh, Stepper): 32 columns of kRowCap rows. Single-body worlds rarely need more
-// than two rows per environment and get 4-row columns (6 KB per warp); worlds with pushable blocks
-// get 8-row columns (12 KB per warp, 14 KB with more than one pushable block). A 65536-environment
-// batch puts 7 64-thread blocks (or one 448-thread block) on each SM.
-template <int NB> struct RowCap { static constexpr int value = NB == 1 ? 4 : 8; };
+// rows (prl_device.cuh, Stepper): 32 columns of RowCap rows. Single-body worlds rarely need more
+// than two rows per environment and get 4-row columns (6 KB per warp). push.json needs 6 or 7 rows
+// in most steps and 8 or 9 in 0.3 % of them: 7-row columns (10.5 KB per warp) keep a 448-thread
+// block under 164 KB of shared memory, which leaves the SM 92 KB of L1 for the manifold records
+// in thread-local memory (8-row columns: 60 KB). More than one pushable block: 8-row columns.
+// A 65536-environment batch puts 7 64-thread blocks (or one 448-thread block) on each SM.
+#ifndef PRL_ROWCAP2
+#define PRL_ROWCAP2 7
+#endif
+template <int NB> struct RowCap { static constexpr int value = NB == 1 ? 4 : (NB == 2 ? PRL_ROWCAP2 : 8); };
 template <int NB, class WT> using SimOf = Stepper<NB, MAXC, WT, RowCap<NB>::value>;
 // Rollouts of large batches run ONE block of 448 threads per SM (the same 14 warps, 148 x 448 >=
 // 65536) with a block barrier at the top of every step: the step is ~4000 straight-line
@@ -115,7 +127,7 @@ __device__ __forceinline__ void env_init(const WT& W, Env<NB>& e) {
 }
 
 template <int NB, class WT>
-__device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, const uint32_t* __restrict__ st, int64_t n, int64_t i) {
+__device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct, const uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto ld = [&](int f) { return __uint_as_float(st[(int64_t)f * n + i]); };
     uint32_t fl = st[(int64_t)F_FLAGS * n + i];
     e.sleeping = fl & 0xffu;
@@ -150,7 +162,7 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, const uint32_t
         uint32_t h = st[(int64_t)f * n + i];
         int slot = direct ? (int)(h & 0xffu) : k;
         if (direct) e.used |= 1u << slot;
-        float* rec = &e.mf[slot][0].x;
+        float* rec = &ct.mf[slot][0].x;
         rec[0] = __uint_as_float(h);
 #pragma unroll 1
         for (int j = 1; j < MF_WORDS; ++j) rec[j] = ld(f + j);
@@ -158,7 +170,7 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, const uint32_t
 }
 
 template <int NB, class WT>
-__device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, uint32_t* __restrict__ st, int64_t n, int64_t i) {
+__device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, const Contacts<>& ct, uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto sf = [&](int f, float v) { st[(int64_t)f * n + i] = __float_as_uint(v); };
     constexpr bool direct = SimOf<NB, WT>::kDirect;
     int count = direct ? __popc(e.used) : e.count;
@@ -181,7 +193,7 @@ __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, uint32_
         int slot = direct ? __ffs((int)left) - 1 : (int)((e.order >> (4 * k)) & 15u);
         left &= left - 1;
         int f = base + MF_WORDS * k;
-        const float* rec = &e.mf[slot][0].x;
+        const float* rec = &ct.mf[slot][0].x;
         st[(int64_t)f * n + i] = __float_as_uint(rec[0]) & 0xfffu;  // pair | npts << 8 (solver-contact count is derived)
 #pragma unroll 1
         for (int j = 1; j < MF_WORDS; ++j) sf(f + j, rec[j]);
@@ -224,12 +236,13 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) step_kernel(const DevW
     const bool live = i < n;
     if (!live) i = n - 1;
     Env<NB> e;
-    env_load(W, e, st, n, i);
+    Contacts<> ct;
+    env_load(W, e, ct, st, n, i);
     float score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
     int win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
     int steps = (int)st[(int64_t)F_STEPS * n + i];
     uint32_t mv = moves ? (moves[i] & 7u) : (uniform_move & 7u);
-    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
+    Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     sim.refresh_solver_contacts();
 #pragma unroll 1
     for (int t = 0;; ++t) {
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) step_kernel(const DevW
     }
     if (!live) return;
     if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);  // more live manifolds than PRL_MAX_CONTACTS: reported by prl_batch_sync
-    env_store(W, e, st, n, i);
+    env_store(W, e, ct, st, n, i);
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
     st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
     st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
@@ -270,8 +283,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     bool live = i < n;  // see step_kernel
     if (!live) i = n - 1;
     Env<NB> e;
+    Contacts<> ct;
     env_init(W, e);
-    Sim sim(W, e, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
+    Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     float score = __int_as_float(0x7f800000);
     int win_step = -1, steps = 0;
     const uint8_t* genome = genomes + i * (int64_t)genome_len;
@@ -289,14 +303,19 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
 #pragma unroll 1
     while (true) {
         sim.detect_pending();
-        if (__syncthreads_and(!(t < total))) break;
+#if defined(PRL_PHASE_TIMING)
+        { long long c_ = clock64(); if (iter == 0) sim.tlast = c_; }
+#endif
+        const bool all_done = __syncthreads_and(!(t < total));
+        PRL_TICK_K(8);
+        if (all_done) break;
         if (BLOCK == kBigBlock && iter > 0 && iter % kRegroupEvery == 0) {
             // ---- regroup: park, sort, pick up (all threads of the block are here, nothing pending)
             int* hist = regroup;
             int* perm_env = regroup + kRegroupKeys;
             int* perm_live = perm_env + kBigBlock;
             if (live) {
-                env_store(W, e, st, n, i);
+                env_store(W, e, ct, st, n, i);
                 st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
                 st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
                 st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
@@ -314,7 +333,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             __syncthreads();
             i = (int64_t)blockIdx.x * BLOCK + perm_env[threadIdx.x];
             live = perm_live[threadIdx.x] != 0;
-            env_load(W, e, st, n, i);
+            env_load(W, e, ct, st, n, i);
             score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
             win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
             steps = (int)st[(int64_t)F_STEPS * n + i];
@@ -325,6 +344,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             rep = t < main_steps ? t % repeat_move : 0;
             gene = g < genome_len ? (genome[g] & 7u) : 0u;
             __syncthreads();  // hist / perm are reused by the next regroup
+            PRL_TICK_K(9);
         }
         ++iter;
         const bool run = t < total;
@@ -344,9 +364,15 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             if (won && early_exit) t = in_genes ? main_steps : total;
         });
     }
+#if defined(PRL_PHASE_TIMING)
+    if (blockIdx.x == 3 && (threadIdx.x & 31u) == 0)
+        printf("warp %2d: broad %lld player-np %lld block-np %lld move %lld select %lld gen %lld sweeps %lld rest %lld barrier %lld regroup %lld\n",
+               (int)(threadIdx.x >> 5), sim.tacc[0] / iter, sim.tacc[1] / iter, sim.tacc[2] / iter, sim.tacc[3] / iter, sim.tacc[4] / iter,
+               sim.tacc[5] / iter, sim.tacc[6] / iter, sim.tacc[7] / iter, sim.tacc[8] / iter, sim.tacc[9] / iter);
+#endif
     if (!live) return;
     if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);  // more live manifolds than PRL_MAX_CONTACTS: reported by prl_batch_sync
-    env_store(W, e, st, n, i);
+    env_store(W, e, ct, st, n, i);
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
     st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
     st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;

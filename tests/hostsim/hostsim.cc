@@ -41,10 +41,12 @@ template <int NB, int PR, class WT>
 static float rollout(const WT& W, const uint8_t* genome, int genome_len, int repeat_move, int number_of_steps,
                      int early_exit, float* traj, int* win_out, int* steps_out, int* overflow) {
     static Env<NB> e;
+    static Contacts<> k;
     init_env(W, e);
+    memset(&k, 0, sizeof k);
     using Sim = Stepper<NB, MAXC, WT, PR>;
     alignas(16) static unsigned char pool[Sim::kWarpBytes + Sim::kPoolPad];
-    Sim sim(W, e, pool);
+    Sim sim(W, e, k, pool);
     float score = INFINITY;
     int win = -1, steps = 0;
     auto record = [&]() {
@@ -127,7 +129,7 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
         static DevWorldSmall S;
         copy_world(S, W);
         if (W.n_bodies == 1) *score = small_pool ? rollout<1, 4>(S, HS_ARGS) : rollout<1, 8>(S, HS_ARGS);
-        else *score = small_pool ? rollout<2, 4>(S, HS_ARGS) : rollout<2, 8>(S, HS_ARGS);
+        else *score = small_pool ? rollout<2, 4>(S, HS_ARGS) : rollout<2, 7>(S, HS_ARGS);
     } else if (W.n_bodies == 1) {
         *score = small_pool ? rollout<1, 4>(W, HS_ARGS) : rollout<1, 8>(W, HS_ARGS);
     } else {
