@@ -239,13 +239,16 @@ PRL_D float cuboid_sat_oneway(v2 he1, v2 he2, const Iso& pos12, v2& best_dir) {
 }
 
 // parry contact_manifold_cuboid_cuboid
-PRL_COLD void contact_cuboid_cuboid_full(Manifold& m, const Iso& pos12, v2 he1, v2 he2, float prediction) {
+// (the out-of-line routines take and return everything BY VALUE: a local whose address is passed
+// to a call lives in memory, hot path included)
+PRL_COLD Manifold contact_cuboid_cuboid_full(Iso pos12, v2 he1, v2 he2, float prediction) {
+    Manifold m = {};
     Iso pos21 = inverse(pos12);
     v2 d1, d2;
     float sep1 = cuboid_sat_oneway(he1, he2, pos12, d1);
-    if (sep1 > prediction) { m.npts = 0; return; }
+    if (sep1 > prediction) return m;
     float sep2 = cuboid_sat_oneway(he2, he1, pos21, d2);
-    if (sep2 > prediction) { m.npts = 0; return; }
+    if (sep2 > prediction) return m;
     v2 best = d1;
     if (sep2 > sep1) best = rot(pos12.c, pos12.s, -d2);
     m.npts = 0;
@@ -258,6 +261,7 @@ PRL_COLD void contact_cuboid_cuboid_full(Manifold& m, const Iso& pos12, v2 he1, 
     face_face_contacts(m, pos12, f1a, f1b, best, f2a, f2b);
     m.n1 = best;
     m.n2 = ln2;
+    return m;
 }
 
 // Closest points between the capsule's inner segment [a,b] and the box [-he,he], in the box
@@ -315,7 +319,8 @@ PRL_D bool segment_box_closest(v2 a, v2 b, v2 he, float& u_out, v2& q_out) {
 
 // parry contact_manifold_pfm_pfm with pfm1 = the capsule's segment (border radius r) and
 // pfm2 = the cuboid: closest points, then segment-vs-support-face clipping, then the radius shift.
-PRL_COLD void contact_capsule_cuboid_full(Manifold& m, const Iso& pos12, float radius, float hh, v2 he2, float prediction) {
+PRL_COLD Manifold contact_capsule_cuboid_full(Iso pos12, float radius, float hh, v2 he2, float prediction) {
+    Manifold m = {};
     const float total_prediction = prediction + radius + 0.0f;
     v2 sa = V(0.0f, -hh), sb = V(0.0f, hh);
     v2 a2 = xform_inv(pos12, sa), b2 = xform_inv(pos12, sb);
@@ -327,7 +332,7 @@ PRL_COLD void contact_capsule_cuboid_full(Manifold& m, const Iso& pos12, float r
         p2_1 = xform(pos12, q);
         v2 dp = p2_1 - p1;
         float n = sqrtf(dot(dp, dp));
-        if (n > total_prediction) return;
+        if (n > total_prediction) return m;
         dir = V(dp.x / n, dp.y / n);
     } else {
         // inner segment inside the box (parry: EPA): minimum face penetration of the deeper endpoint
@@ -367,22 +372,23 @@ PRL_COLD void contact_capsule_cuboid_full(Manifold& m, const Iso& pos12, float r
     }
     m.n1 = dir;
     m.n2 = n2;
+    return m;
 }
 
 // hot path of both contact routines: the cached manifold usually survives (persistence first)
 PRL_D void contact_cuboid_cuboid(Manifold& m, const Iso& pos12, v2 he1, v2 he2, float prediction) {
-    if (!manifold_try_update(m, pos12)) contact_cuboid_cuboid_full(m, pos12, he1, he2, prediction);
+    if (!manifold_try_update(m, pos12)) m = contact_cuboid_cuboid_full(pos12, he1, he2, prediction);
 }
 PRL_D void contact_capsule_cuboid(Manifold& m, const Iso& pos12, float radius, float hh, v2 he2, float prediction) {
-    if (!manifold_try_update(m, pos12)) contact_capsule_cuboid_full(m, pos12, radius, hh, he2, prediction);
+    if (!manifold_try_update(m, pos12)) m = contact_capsule_cuboid_full(pos12, radius, hh, he2, prediction);
 }
 
 // sin and cos of a pushable block's rotation increment; kept out of line so the pose update of
 // every body shares one copy of the argument reduction
 #if defined(__CUDA_ARCH__)
-static __device__ __noinline__ void libm_sincosf(float x, float& s, float& c) { s = libm_sinf(x); c = libm_cosf(x); }
+static __device__ __noinline__ v2 libm_sincosf(float x) { return V(libm_sinf(x), libm_cosf(x)); }  // (sin, cos)
 #else
-inline void libm_sincosf(float x, float& s, float& c) { s = libm_sinf(x); c = libm_cosf(x); }
+inline v2 libm_sincosf(float x) { return V(libm_sinf(x), libm_cosf(x)); }
 #endif
 
 // rapier RigidBodyVelocity::integrate with local_com = origin:
@@ -392,7 +398,7 @@ inline void libm_sincosf(float x, float& s, float& c) { s = libm_sinf(x); c = li
 PRL_D Iso integrate_pose(v2 linvel, float angvel, const Iso& init, float dt, bool locked) {
     v2 com = init.t;
     float rc = 1.0f, rs = 0.0f;
-    if (!locked) libm_sincosf(angvel * dt, rs, rc);
+    if (!locked) { v2 sc = libm_sincosf(angvel * dt); rs = sc.x; rc = sc.y; }
     v2 tr = linvel * dt;
     v2 t = com + tr;
     t = t + rot(rc, rs, -com);
