@@ -564,6 +564,11 @@ struct Stepper {
         return c;
     }
     PRL_D int ns_of(int slot) const { return (int)((e.sns >> (2 * slot)) & 3u); }
+    // bodies of pair p's colliders from the packed pair word: -1 for a fixed collider
+    PRL_D static int info_b1(uint32_t info) { return (int)(int8_t)((info >> 16) & 0xffu); }
+    PRL_D static int info_b2(uint32_t info) { return (int)(int8_t)(info >> 24); }
+    PRL_D static int info_c1(uint32_t info) { return (int)(info & 0xffu); }
+    PRL_D static int info_c2(uint32_t info) { return (int)((info >> 8) & 0xffu); }
     PRL_D int pair_at(int k) const { return pair_of(slot_at(k)); }
     PRL_D Iso body_pose(int b) const { Iso p; p.t = V(sel(e.x, b), sel(e.y, b)); p.c = sel(e.c, b); p.s = sel(e.s, b); return p; }
     PRL_D Iso collider_pose(int c) const {
@@ -571,6 +576,13 @@ struct Stepper {
         if (b >= 0) return body_pose(b);
         Iso p; p.t = V(W.cx[c], W.cy[c]); p.c = W.cc[c]; p.s = W.cs[c];
         return p;
+    }
+    // pose of pair p's collider with body index b (b < 0: the pair's fixed collider)
+    PRL_D Iso pair_collider_pose(int p, int b) const {
+        if (b >= 0) return body_pose(b);
+        const f4 q = *reinterpret_cast<const f4*>(W.pair_pose[p]);
+        Iso r; r.t = V(q.x, q.y); r.c = q.z; r.s = q.w;
+        return r;
     }
     PRL_D void wake_strong(int b) { e.sleeping &= ~(1u << b); put(e.timer, b, 0.0f); }
 
@@ -601,7 +613,7 @@ struct Stepper {
             }
         }
         if (SCAN && gs_n >= 0) {  // a player pair: floor contacts among its solver contacts (common.rs:234-238)
-            const int body = W.body_of[W.pair_c2[pair]];
+            const int body = info_b2(W.pair_info[pair]);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
                 if (k < ns) {
@@ -740,7 +752,7 @@ struct Stepper {
             int slot = it_slot(it);
             int p = pair_of(slot), ns = ns_of(slot);
             if (p >= W.n_player_pairs) break;
-            int body = W.body_of[W.pair_c2[p]];
+            int body = info_b2(W.pair_info[p]);
             f4 s0 = k.sc[slot][0], s1 = k.sc[slot][1];
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
@@ -779,7 +791,7 @@ struct Stepper {
                 int slot = it_slot(it);
                 int ns = ns_of(slot);
                 if (pair_of(slot) >= W.n_player_pairs) break;
-                int body = W.body_of[W.pair_c2[pair_of(slot)]];
+                int body = info_b2(W.pair_info[pair_of(slot)]);
                 f4 s0 = k.sc[slot][0], s1 = k.sc[slot][1];
 #pragma unroll 1
                 for (int i = 0; i < ns; ++i) {
@@ -827,7 +839,8 @@ struct Stepper {
                         int slot = it_slot(it);
                         if (ns_of(slot) == 0) continue;
                         int p = pair_of(slot);
-                        int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
+                        const uint32_t info = W.pair_info[p];
+                        int b1 = info_b1(info), b2 = info_b2(info);
                         if (b1 < 0 || b2 < 0) continue;
                         uint32_t m1 = 1u << b1, m2 = 1u << b2;
                         if ((reached & m1) || (reached & m2)) reached |= m1 | m2;
@@ -851,11 +864,11 @@ struct Stepper {
     // appends one row per solver contact. A one-body ("ground") constraint is written as a
     // two-body row against the pseudo body kGround (zero velocity, zero inverse mass, zero
     // angular response), which evaluates to the same values as rapier's ground formulas.
-    PRL_D int generate_constraint(int slot, int nrows) {
+    PRL_D int generate_constraint(int slot, int nrows, const f4& s0, const f4& s1) {
         int p = pair_of(slot), ns = ns_of(slot);
-        int h1 = W.body_of[W.pair_c1[p]], h2 = W.body_of[W.pair_c2[p]];
+        const uint32_t info = W.pair_info[p];
+        int h1 = info_b1(info), h2 = info_b2(info);
         bool two_body = h1 >= 0 && h2 >= 0;
-        f4 s0 = k.sc[slot][0], s1 = k.sc[slot][1];
         v2 normal = V(s0.x, s0.y);
         v2 dir1;
         if (two_body) dir1 = -normal;
@@ -1101,7 +1114,8 @@ struct Stepper {
                 int ns = ns_of(slot);
                 if (ns == 0) continue;
                 int p = pair_of(slot);
-                int h1 = W.body_of[W.pair_c1[p]], h2 = W.body_of[W.pair_c2[p]];
+                const uint32_t info = W.pair_info[p];
+                int h1 = info_b1(info), h2 = info_b2(info);
                 bool two_body = h1 >= 0 && h2 >= 0;
                 if ((pass == 0) != two_body) continue;
                 bool awake1 = h1 >= 0 && ((active >> h1) & 1u);
@@ -1123,8 +1137,23 @@ struct Stepper {
         ent0 = first_entry;
         stride = entry_stride;
         int nrows = 0;
+        {
+            // the next manifold's solver contacts are fetched from thread-local memory while the
+            // rows of the current one are built
+            f4 n0 = {}, n1 = {};
+            if (ncons > 0) { const int s0_ = (int)(cons & 15u); n0 = k.sc[s0_][0]; n1 = k.sc[s0_][1]; }
 #pragma unroll 1
-        for (int i = 0; i < ncons; ++i) nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows);
+            for (int i = 0; i < ncons; ++i) {
+                const f4 c0 = n0, c1 = n1;
+#if defined(PRL_SC_PREFETCH)
+                if (i + 1 < ncons) { const int sn = (int)((cons >> (4 * (i + 1))) & 15u); n0 = k.sc[sn][0]; n1 = k.sc[sn][1]; }
+                nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows, c0, c1);
+#else
+                nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows, c0, c1);
+                if (i + 1 < ncons) { const int sn = (int)((cons >> (4 * (i + 1))) & 15u); n0 = k.sc[sn][0]; n1 = k.sc[sn][1]; }
+#endif
+            }
+        }
         PRL_TICK(5);
         float dlx[NB], dly[NB], da[NB];
 #pragma unroll
@@ -1194,17 +1223,19 @@ struct Stepper {
         return active;
     }
 
-    // loosened AABB overlap of pair p and whether one of its colliders moved
+    // loosened AABB overlap of pair p and whether one of its colliders moved. A pair has at most
+    // one fixed collider, whose box comes with the pair.
     PRL_D bool pair_overlaps(int p, uint32_t moved, bool all, const float (&bmnx)[NB], const float (&bmny)[NB], const float (&bmxx)[NB],
                              const float (&bmxy)[NB], bool& modified) const {
-        int c1 = W.pair_c1[p], c2 = W.pair_c2[p];
-        int b1 = W.body_of[c1], b2 = W.body_of[c2];
+        const uint32_t info = W.pair_info[p];
+        const f4 box = *reinterpret_cast<const f4*>(W.pair_box[p]);
+        int b1 = info_b1(info), b2 = info_b2(info);
         modified = all || (b1 >= 0 && ((moved >> b1) & 1u)) || (b2 >= 0 && ((moved >> b2) & 1u));
         float amnx, amny, amxx, amxy, qmnx, qmny, qmxx, qmxy;
         if (b1 >= 0) { amnx = sel(bmnx, b1); amny = sel(bmny, b1); amxx = sel(bmxx, b1); amxy = sel(bmxy, b1); }
-        else { amnx = W.amnx[c1]; amny = W.amny[c1]; amxx = W.amxx[c1]; amxy = W.amxy[c1]; }
+        else { amnx = box.x; amny = box.y; amxx = box.z; amxy = box.w; }
         if (b2 >= 0) { qmnx = sel(bmnx, b2); qmny = sel(bmny, b2); qmxx = sel(bmxx, b2); qmxy = sel(bmxy, b2); }
-        else { qmnx = W.amnx[c2]; qmny = W.amny[c2]; qmxx = W.amxx[c2]; qmxy = W.amxy[c2]; }
+        else { qmnx = box.x; qmny = box.y; qmxx = box.z; qmxy = box.w; }
         return amnx <= qmxx && qmnx <= amxx && amny <= qmxy && qmny <= amxy;
     }
 
@@ -1250,7 +1281,8 @@ struct Stepper {
                 if (modified && !ov && (e.used & bit)) {
                     // NarrowPhase::remove_pair wakes both bodies if the pair had an active contact
                     if (ns_of(p) != 0) {
-                        int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
+                        const uint32_t info = W.pair_info[p];
+                        int b1 = info_b1(info), b2 = info_b2(info);
                         if (b1 >= 0) wake_strong(b1);
                         if (b2 >= 0) wake_strong(b2);
                     }
@@ -1265,13 +1297,13 @@ struct Stepper {
 #pragma unroll 1
             for (uint32_t m_ = cand & pmask; m_ != 0; m_ &= m_ - 1) {
                 int p = first_bit_from(m_, 0);
-                int c2 = W.pair_c2[p];
+                const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
                 Manifold m;
                 if (e.used & (1u << p)) load_manifold(p, m);
                 else m.npts = 0;
                 Iso pose1 = body_pose(0);
-                Iso pos12 = inv_mul(pose1, collider_pose(c2));
-                contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(W.hx[c2], W.hy[c2]), W.prediction);
+                Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(W.pair_info[p])));
+                contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(he.z, he.w), W.prediction);
                 commit_direct<true>(p, m, pose1);
             }
             PRL_TICK(1);
@@ -1279,13 +1311,14 @@ struct Stepper {
 #pragma unroll 1
                 for (uint32_t m_ = cand & ~pmask; m_ != 0; m_ &= m_ - 1) {
                     int p = first_bit_from(m_, 0);
-                    int c1 = W.pair_c1[p], c2 = W.pair_c2[p];
+                    const uint32_t info = W.pair_info[p];
+                    const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
                     Manifold m;
                     if (e.used & (1u << p)) load_manifold(p, m);
                     else m.npts = 0;
-                    Iso pose1 = collider_pose(c1);
-                    Iso pos12 = inv_mul(pose1, collider_pose(c2));
-                    contact_cuboid_cuboid(m, pos12, V(W.hx[c1], W.hy[c1]), V(W.hx[c2], W.hy[c2]), W.prediction);
+                    Iso pose1 = pair_collider_pose(p, info_b1(info));
+                    Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(info)));
+                    contact_cuboid_cuboid(m, pos12, V(he.x, he.y), V(he.z, he.w), W.prediction);
                     commit_direct(p, m, pose1);
                 }
             }
@@ -1307,7 +1340,8 @@ struct Stepper {
                 bool have = k < e.count && pair_at(k) == p;
                 if (modified && !ov && have) {
                     if (ns_of(slot_at(k)) != 0) {
-                        int b1 = W.body_of[W.pair_c1[p]], b2 = W.body_of[W.pair_c2[p]];
+                        const uint32_t info = W.pair_info[p];
+                        int b1 = info_b1(info), b2 = info_b2(info);
                         if (b1 >= 0) wake_strong(b1);
                         if (b2 >= 0) wake_strong(b2);
                     }
@@ -1336,13 +1370,13 @@ struct Stepper {
             while (k < e.count && pair_at(k) < p) ++k;
             bool have = k < e.count && pair_at(k) == p;
             int slot = have ? slot_at(k) : -1;
-            int c2 = W.pair_c2[p];
+            const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
             Manifold m;
             if (have) load_manifold(slot, m);
             else m.npts = 0;
             Iso pose1 = body_pose(0);
-            Iso pos12 = inv_mul(pose1, collider_pose(c2));
-            contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(W.hx[c2], W.hy[c2]), W.prediction);
+            Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(W.pair_info[p])));
+            contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(he.z, he.w), W.prediction);
             k = commit<true>(p, k, have, slot, m, pose1);
         }
         if (NB > 1) {
@@ -1352,13 +1386,14 @@ struct Stepper {
                 while (k < e.count && pair_at(k) < p) ++k;
                 bool have = k < e.count && pair_at(k) == p;
                 int slot = have ? slot_at(k) : -1;
-                int c1 = W.pair_c1[p], c2 = W.pair_c2[p];
+                const uint32_t info = W.pair_info[p];
+                const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
                 Manifold m;
                 if (have) load_manifold(slot, m);
                 else m.npts = 0;
-                Iso pose1 = collider_pose(c1);
-                Iso pos12 = inv_mul(pose1, collider_pose(c2));
-                contact_cuboid_cuboid(m, pos12, V(W.hx[c1], W.hy[c1]), V(W.hx[c2], W.hy[c2]), W.prediction);
+                Iso pose1 = pair_collider_pose(p, info_b1(info));
+                Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(info)));
+                contact_cuboid_cuboid(m, pos12, V(he.x, he.y), V(he.z, he.w), W.prediction);
                 k = commit(p, k, have, slot, m, pose1);
             }
         }

@@ -99,7 +99,13 @@ __device__ __forceinline__ void stage_world(WT* dst, const DevWorld* __restrict_
         dst->ccd_thickness[b] = src->ccd_thickness[b]; dst->gdv_x[b] = src->gdv_x[b]; dst->gdv_y[b] = src->gdv_y[b];
         dst->collider_of[b] = src->collider_of[b];
     }
-    for (int p = t; p < src->n_pairs; p += nt) { dst->pair_c1[p] = src->pair_c1[p]; dst->pair_c2[p] = src->pair_c2[p]; }
+    for (int p = t; p < src->n_pairs; p += nt) {
+        dst->pair_c1[p] = src->pair_c1[p]; dst->pair_c2[p] = src->pair_c2[p]; dst->pair_info[p] = src->pair_info[p];
+        dst->pair_box[p][0] = src->pair_box[p][0]; dst->pair_box[p][1] = src->pair_box[p][1];
+        dst->pair_box[p][2] = src->pair_box[p][2]; dst->pair_box[p][3] = src->pair_box[p][3];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { dst->pair_pose[p][q] = src->pair_pose[p][q]; dst->pair_he[p][q] = src->pair_he[p][q]; }
+    }
     for (int g = t; g < src->n_goals; g += nt) {
         dst->gx[g] = src->gx[g]; dst->gy[g] = src->gy[g]; dst->ghw[g] = src->ghw[g]; dst->ghh[g] = src->ghh[g];
         dst->gxax[g] = src->gxax[g]; dst->gxay[g] = src->gxay[g]; dst->gyax[g] = src->gyax[g]; dst->gyay[g] = src->gyay[g];
@@ -300,12 +306,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     int g = 0, rep = 0, t = 0, iter = 0;
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
     int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes + Sim::kPoolPad);  // only if BLOCK == kBigBlock
+#if defined(PRL_PHASE_TIMING)
+    sim.tlast = clock64();
+#endif
 #pragma unroll 1
     while (true) {
         sim.detect_pending();
-#if defined(PRL_PHASE_TIMING)
-        { long long c_ = clock64(); if (iter == 0) sim.tlast = c_; }
-#endif
         const bool all_done = __syncthreads_and(!(t < total));
         PRL_TICK_K(8);
         if (all_done) break;

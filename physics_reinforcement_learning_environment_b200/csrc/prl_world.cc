@@ -158,6 +158,16 @@ int build_dev_world(prl_world* w) {
             if (np >= PRL_MAX_PAIRS) { set_error("world needs more than PRL_MAX_PAIRS=%d candidate collider pairs", PRL_MAX_PAIRS); return PRL_ERR_CAPACITY; }
             d.pair_c1[np] = (uint8_t)a;
             d.pair_c2[np] = (uint8_t)b;
+            d.pair_info[np] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)(d.body_of[a] & 0xff) << 16) | ((uint32_t)(d.body_of[b] & 0xff) << 24);
+            const int fixed = d.body_of[a] < 0 ? a : (d.body_of[b] < 0 ? b : -1);
+            for (int q = 0; q < 4; ++q) d.pair_box[np][q] = d.pair_pose[np][q] = 0.0f;
+            d.pair_he[np][0] = d.hx[a]; d.pair_he[np][1] = d.hy[a]; d.pair_he[np][2] = d.hx[b]; d.pair_he[np][3] = d.hy[b];
+            if (fixed >= 0) {
+                d.pair_pose[np][0] = d.cx[fixed]; d.pair_pose[np][1] = d.cy[fixed];
+                d.pair_pose[np][2] = d.cc[fixed]; d.pair_pose[np][3] = d.cs[fixed];
+                d.pair_box[np][0] = d.amnx[fixed]; d.pair_box[np][1] = d.amny[fixed];
+                d.pair_box[np][2] = d.amxx[fixed]; d.pair_box[np][3] = d.amxy[fixed];
+            }
             if (a == 0) ++npp;
             ++np;
         }

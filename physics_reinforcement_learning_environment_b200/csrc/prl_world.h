@@ -44,6 +44,15 @@ struct alignas(16) DevWorldT {
     int32_t collider_of[MAXB];
     // candidate pairs, ascending (collider1, collider2), fixed-fixed excluded
     uint8_t pair_c1[MP], pair_c2[MP];
+    // the same per pair in one word, so the per-step walks over pairs need no dependent table
+    // look-ups: collider1 | collider2 << 8 | body1 << 16 | body2 << 24 (body 0xff: fixed collider),
+    // and the loosened AABB (min x, min y, max x, max y) of the pair's fixed collider, if any
+    // pair_pose: pose (x, y, cos, sin) of that fixed collider; pair_he: half extents of collider1
+    // and collider2 (hx1, hy1, hx2, hy2)
+    uint32_t pair_info[MP];
+    alignas(16) float pair_box[MP][4];
+    alignas(16) float pair_pose[MP][4];
+    alignas(16) float pair_he[MP][4];
     // goals (common.rs:148-157, 175-195)
     float gx[MG], gy[MG], ghw[MG], ghh[MG];        // centre, width/2, height/2
     float gxax[MG], gxay[MG], gyax[MG], gyay[MG];  // Quat::from_rotation_z(rot) * X / Y, truncated

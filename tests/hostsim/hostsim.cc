@@ -106,7 +106,10 @@ static void copy_world(WT& d, const DevWorld& s) {
         d.inv_mass[b] = s.inv_mass[b]; d.inv_inertia_sqrt[b] = s.inv_inertia_sqrt[b]; d.ccd_thickness[b] = s.ccd_thickness[b];
         d.gdv_x[b] = s.gdv_x[b]; d.gdv_y[b] = s.gdv_y[b]; d.collider_of[b] = s.collider_of[b];
     }
-    for (int p = 0; p < s.n_pairs; ++p) { d.pair_c1[p] = s.pair_c1[p]; d.pair_c2[p] = s.pair_c2[p]; }
+    for (int p = 0; p < s.n_pairs; ++p) {
+        d.pair_c1[p] = s.pair_c1[p]; d.pair_c2[p] = s.pair_c2[p]; d.pair_info[p] = s.pair_info[p];
+        for (int q = 0; q < 4; ++q) { d.pair_box[p][q] = s.pair_box[p][q]; d.pair_pose[p][q] = s.pair_pose[p][q]; d.pair_he[p][q] = s.pair_he[p][q]; }
+    }
     for (int g = 0; g < s.n_goals; ++g) {
         d.gx[g] = s.gx[g]; d.gy[g] = s.gy[g]; d.ghw[g] = s.ghw[g]; d.ghh[g] = s.ghh[g];
         d.gxax[g] = s.gxax[g]; d.gxay[g] = s.gxay[g]; d.gyax[g] = s.gyax[g]; d.gyay[g] = s.gyay[g];
