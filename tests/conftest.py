@@ -53,6 +53,22 @@ def synth_world(n_obstacles=63, seed=64):
     return {"player_position": [0.0, 0.0], "objects": objs}
 
 
+def many_supports_world(n_posts=6):
+    """One pushable plank resting on n fixed posts. Two solver contacts per post plus the
+    player's make an environment need more constraint rows than one column of the solver's row
+    storage holds, so the warps of the kernels solve in rounds (prl_kernels.cuh,
+    solve_in_rounds): 6 posts = 13 candidate pairs, the small-world kernel (7-row columns, 12-14
+    rows: two rounds); 8 posts = the general kernel (8-row columns, 16-18 rows: four rounds)."""
+    objs = []
+    for i in range(n_posts):
+        objs.append({"object": {"Block": {"fixed": True}}, "position": [-150.0 + 60.0 * i, -40.0, float(i + 1)],
+                     "scale": [30.0, 40.0], "rotation": 0.0})
+    objs.append({"object": {"Block": {"fixed": False}}, "position": [-150.0 + 30.0 * (n_posts - 1), -14.0, float(n_posts + 1)],
+                 "scale": [60.0 * n_posts + 40.0, 12.0], "rotation": 0.0})
+    objs.append({"object": "Goal", "position": [60.0 * n_posts - 100.0, 30.0, float(n_posts + 2)], "scale": [60.0, 60.0], "rotation": 0.0})
+    return {"player_position": [-100.0, 24.0], "objects": objs}
+
+
 def random_genomes(n, genome_len, seed):
     return np.random.Generator(np.random.Philox(seed)).integers(0, 8, size=(n, genome_len), dtype=np.uint8)
 

@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ROOT, WORLDS, n_bodies_of, random_genomes, random_world, synth_world, world_dict
+from conftest import ROOT, WORLDS, many_supports_world, n_bodies_of, random_genomes, random_world, synth_world, world_dict
 from oracle.binding import OracleEnv
 
 _hs = None
@@ -57,6 +57,16 @@ def test_trajectories_bit_exact(name):
     for g in genomes:
         t, _, _, _ = host_rollout(world, g, 20, 1000, False)
         o = oracle_traj(world, g, 20, 1000)
+        assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
+
+
+@pytest.mark.parametrize("n_posts", [6, 8])
+def test_many_constraint_rows(n_posts):
+    """12-18 constraint rows per environment (a plank on many posts)."""
+    world = many_supports_world(n_posts)
+    for g in random_genomes(3, 30, 41 + n_posts):
+        t, _, _, _ = host_rollout(world, g, 20, 600, False)
+        o = oracle_traj(world, g, 20, 600)
         assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
 
 

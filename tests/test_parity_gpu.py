@@ -10,7 +10,7 @@ import pytest
 
 import physics_reinforcement_learning_environment_b200 as prl
 from physics_reinforcement_learning_environment_b200 import _lib
-from conftest import WORLDS, random_genomes, random_world, synth_world, world_dict, world_text
+from conftest import WORLDS, many_supports_world, random_genomes, random_world, synth_world, world_dict, world_text
 from oracle import binding as oracle
 from oracle.binding import OracleEnv
 
@@ -111,6 +111,30 @@ def test_two_pushable_blocks_rotations_negative_scales():
         for t in range(steps):
             o.step(int(genomes[i][t // repeat]))
         assert np.array_equal(bits(st[i]), bits(o.state()))
+
+
+@pytest.mark.parametrize("n_posts", [6, 8])
+def test_more_rows_than_a_column_holds_solves_in_rounds(n_posts):
+    """A plank on many posts needs 12-18 constraint rows per environment: more than a column of
+    the warp's row storage, so the lanes of a warp take turns (two / four rounds). Rollouts and
+    single steps must still match the oracle bit for bit."""
+    world = many_supports_world(n_posts)
+    n, L, repeat, steps = 200, 30, 20, 600
+    genomes = random_genomes(n, L, 41 + n_posts)
+    env = prl.BatchedEnvironment(prl.World.from_json(json.dumps(world)), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    env.sync()
+    rs, rw, _ = oracle.rollout_batch(world, genomes, repeat, steps, False, n_threads=os.cpu_count())
+    assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
+    env.reset()
+    o = [OracleEnv(world) for _ in range(3)]
+    for t in range(120):
+        env.step(np.ascontiguousarray(genomes[:, t // repeat]))
+        for i in range(3):
+            o[i].step(int(genomes[i][t // repeat]))
+    st = env.state(0, 3)
+    for i in range(3):
+        assert np.array_equal(bits(st[i]), bits(o[i].state()))
 
 
 def test_result_is_independent_of_batch_size_and_neighbours():
