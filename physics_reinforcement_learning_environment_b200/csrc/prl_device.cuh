@@ -1271,26 +1271,33 @@ struct Stepper {
             }
         }
         if (kDirect) {
-            // slot == pair: the broad phase leaves a bit mask of narrow-phase candidates
-            uint32_t cand = 0;
-#pragma unroll 1
+            // slot == pair: the broad phase is a branch-free pass over the pairs that leaves bit
+            // masks -- overlapping pairs, and (from the world's body -> pairs table) pairs with a
+            // moved collider -- so its table look-ups overlap instead of waiting for each other
+            uint32_t ov = 0;
+#pragma unroll 4
             for (int p = 0; p < W.n_pairs; ++p) {
                 bool modified;
-                bool ov = pair_overlaps(p, moved, all, bmnx, bmny, bmxx, bmxy, modified);
-                const uint32_t bit = 1u << p;
-                if (modified && !ov && (e.used & bit)) {
-                    // NarrowPhase::remove_pair wakes both bodies if the pair had an active contact
-                    if (ns_of(p) != 0) {
-                        const uint32_t info = W.pair_info[p];
-                        int b1 = info_b1(info), b2 = info_b2(info);
-                        if (b1 >= 0) wake_strong(b1);
-                        if (b2 >= 0) wake_strong(b2);
-                    }
-                    e.used &= ~bit;
-                    e.sns &= ~(3u << (2 * p));
-                }
-                if (modified && ov) cand |= bit;
+                if (pair_overlaps(p, moved, all, bmnx, bmny, bmxx, bmxy, modified)) ov |= 1u << p;
             }
+            uint32_t mod = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) if (all || ((moved >> b) & 1u)) mod |= W.body_pairs[b];
+            // a pair that left the broad phase drops its manifold; NarrowPhase::remove_pair wakes
+            // both bodies if the pair had an active contact
+#pragma unroll 1
+            for (uint32_t stale = mod & ~ov & e.used; stale != 0; stale &= stale - 1) {
+                const int p = first_bit_from(stale, 0);
+                if (ns_of(p) != 0) {
+                    const uint32_t info = W.pair_info[p];
+                    int b1 = info_b1(info), b2 = info_b2(info);
+                    if (b1 >= 0) wake_strong(b1);
+                    if (b2 >= 0) wake_strong(b2);
+                }
+                e.used &= ~(1u << p);
+                e.sns &= ~(3u << (2 * p));
+            }
+            const uint32_t cand = mod & ov;
             PRL_TICK(0);
             // narrow phase on "my i-th candidate": player pairs (capsule-cuboid) first, then block pairs
             const uint32_t pmask = (1u << W.n_player_pairs) - 1u;

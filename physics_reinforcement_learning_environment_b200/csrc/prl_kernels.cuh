@@ -97,7 +97,7 @@ __device__ __forceinline__ void stage_world(WT* dst, const DevWorld* __restrict_
     for (int b = t; b < MAXB; b += nt) {
         dst->inv_mass[b] = src->inv_mass[b]; dst->inv_inertia_sqrt[b] = src->inv_inertia_sqrt[b];
         dst->ccd_thickness[b] = src->ccd_thickness[b]; dst->gdv_x[b] = src->gdv_x[b]; dst->gdv_y[b] = src->gdv_y[b];
-        dst->collider_of[b] = src->collider_of[b];
+        dst->collider_of[b] = src->collider_of[b]; dst->body_pairs[b] = src->body_pairs[b];
     }
     for (int p = t; p < src->n_pairs; p += nt) {
         dst->pair_c1[p] = src->pair_c1[p]; dst->pair_c2[p] = src->pair_c2[p]; dst->pair_info[p] = src->pair_info[p];

@@ -152,6 +152,7 @@ int build_dev_world(prl_world* w) {
     // candidate collider pairs in ascending (collider1, collider2) order; two parent-less
     // colliders never collide
     int np = 0, npp = 0;
+    for (int b = 0; b < MAXB; ++b) d.body_pairs[b] = 0;
     for (int a = 0; a < d.n_colliders; ++a)
         for (int b = a + 1; b < d.n_colliders; ++b) {
             if (d.body_of[a] < 0 && d.body_of[b] < 0) continue;
@@ -159,6 +160,10 @@ int build_dev_world(prl_world* w) {
             d.pair_c1[np] = (uint8_t)a;
             d.pair_c2[np] = (uint8_t)b;
             d.pair_info[np] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)(d.body_of[a] & 0xff) << 16) | ((uint32_t)(d.body_of[b] & 0xff) << 24);
+            if (np < 32) {
+                if (d.body_of[a] >= 0) d.body_pairs[d.body_of[a]] |= 1u << np;
+                if (d.body_of[b] >= 0) d.body_pairs[d.body_of[b]] |= 1u << np;
+            }
             const int fixed = d.body_of[a] < 0 ? a : (d.body_of[b] < 0 ? b : -1);
             for (int q = 0; q < 4; ++q) d.pair_box[np][q] = d.pair_pose[np][q] = 0.0f;
             d.pair_he[np][0] = d.hx[a]; d.pair_he[np][1] = d.hy[a]; d.pair_he[np][2] = d.hx[b]; d.pair_he[np][3] = d.hy[b];

@@ -42,6 +42,7 @@ struct alignas(16) DevWorldT {
     float inv_mass[MAXB], inv_inertia_sqrt[MAXB], ccd_thickness[MAXB];
     float gdv_x[MAXB], gdv_y[MAXB];        // 0 + (force * inv_mass) * dt with force = mass * gravity
     int32_t collider_of[MAXB];
+    uint32_t body_pairs[MAXB];             // bit p = candidate pair p involves this body (first 32 pairs)
     // candidate pairs, ascending (collider1, collider2), fixed-fixed excluded
     uint8_t pair_c1[MP], pair_c2[MP];
     // the same per pair in one word, so the per-step walks over pairs need no dependent table

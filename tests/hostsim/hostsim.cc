@@ -104,7 +104,7 @@ static void copy_world(WT& d, const DevWorld& s) {
     }
     for (int b = 0; b < MAXB; ++b) {
         d.inv_mass[b] = s.inv_mass[b]; d.inv_inertia_sqrt[b] = s.inv_inertia_sqrt[b]; d.ccd_thickness[b] = s.ccd_thickness[b];
-        d.gdv_x[b] = s.gdv_x[b]; d.gdv_y[b] = s.gdv_y[b]; d.collider_of[b] = s.collider_of[b];
+        d.gdv_x[b] = s.gdv_x[b]; d.gdv_y[b] = s.gdv_y[b]; d.collider_of[b] = s.collider_of[b]; d.body_pairs[b] = s.body_pairs[b];
     }
     for (int p = 0; p < s.n_pairs; ++p) {
         d.pair_c1[p] = s.pair_c1[p]; d.pair_c2[p] = s.pair_c2[p]; d.pair_info[p] = s.pair_info[p];
