@@ -327,6 +327,10 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
         // blocks. Only the kernels with pushable blocks gain (their step is twice the code; the
         // single-body kernels measured 10-13 % slower with the per-step barrier).
         const bool big = b->n >= (int64_t)b->sm_count * kBigBlock / 2;
+        // a population too small to give every SM a 64-thread block (config C2: 4096 agents) runs one
+        // warp per block, so that it spreads over twice as many SMs: such a rollout is bound by the
+        // latency of a single warp's step, not by throughput
+        const bool tiny = (b->n + kBlock - 1) / kBlock < (int64_t)b->sm_count;
         cudaError_t le = cudaSuccess;
 #define PRL_ROLLOUT(NB_, WT_, BLOCK_)                                                                                     \
     do {                                                                                                                  \
@@ -342,9 +346,13 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
                 b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw, b->overflow); \
     } while (0)
         switch (pick_variant(b->host_world)) {
-            case V1_SMALL: PRL_ROLLOUT(1, DevWorldSmall, kBlock); break;
-            case V2_SMALL: if (big) PRL_ROLLOUT(2, DevWorldSmall, kBigBlock); else PRL_ROLLOUT(2, DevWorldSmall, kBlock); break;
-            case V1_BIG: PRL_ROLLOUT(1, DevWorld, kBlock); break;
+            case V1_SMALL: if (tiny) PRL_ROLLOUT(1, DevWorldSmall, kWarpBlock); else PRL_ROLLOUT(1, DevWorldSmall, kBlock); break;
+            case V2_SMALL:
+                if (big) PRL_ROLLOUT(2, DevWorldSmall, kBigBlock);
+                else if (tiny) PRL_ROLLOUT(2, DevWorldSmall, kWarpBlock);
+                else PRL_ROLLOUT(2, DevWorldSmall, kBlock);
+                break;
+            case V1_BIG: if (tiny) PRL_ROLLOUT(1, DevWorld, kWarpBlock); else PRL_ROLLOUT(1, DevWorld, kBlock); break;
             default: if (big) PRL_ROLLOUT(MAXB, DevWorld, kBigBlock); else PRL_ROLLOUT(MAXB, DevWorld, kBlock); break;
         }
 #undef PRL_ROLLOUT

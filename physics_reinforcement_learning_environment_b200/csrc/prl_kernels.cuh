@@ -22,6 +22,7 @@
 namespace prl {
 
 constexpr int kBlock = 64;
+constexpr int kWarpBlock = 32;  // rollouts of populations too small to fill the SMs with 64-thread blocks
 // Shared memory of a block: the world tables plus, per warp, the planes of velocity-constraint
 // rows (prl_device.cuh, Stepper): 32 columns of RowCap rows. Single-body worlds rarely need more
 // than two rows per environment and get 4-row columns (6 KB per warp). push.json needs 6 or 7 rows
