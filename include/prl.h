@@ -129,6 +129,17 @@ int prl_batch_rollout(prl_batch*, const uint8_t* genomes, int32_t genome_len, in
  * (the GA's score, main.rs:50), 1-based step at which won() first became true (-1: never) and
  * the number of steps taken. Host or device buffers; any may be NULL. Synchronises. */
 int prl_batch_rollout_info(prl_batch*, float* out_score, int32_t* out_step_of_win, int32_t* out_steps);
+/* Replay for the viewers (train.rs:132-159: `update_visualization` steps a fresh Environment with
+ * `agent.get_move()` once per frame and copies every body's transform to its sprite): n fresh
+ * from_world environments play one GeneticAgent each (main.rs:276-284: genes repeated
+ * repeat_move times, then Move::default() forever; no early exit) for number_of_steps steps in ONE
+ * launch, and every body is recorded after every step. Independent of the batch's own
+ * environments (only its world, device and stream are used).
+ * genomes: n x genome_len Moves. out_state: number_of_steps x n x n_bodies x 9 floats (layout of
+ * prl_batch_get_state); out_distance: number_of_steps x n floats (distance_to_goals, +inf without
+ * goals); out_won: number_of_steps x n bytes. Host or device buffers; any output may be NULL. */
+int prl_batch_trajectory(prl_batch*, int64_t n, const uint8_t* genomes, int32_t genome_len, int32_t repeat_move,
+                         int32_t number_of_steps, float* out_state, float* out_distance, uint8_t* out_won);
 /* wait for the handle's stream; returns PRL_ERR_OVERFLOW if any environment needed more than
  * PRL_MAX_CONTACTS simultaneous contact manifolds since the last reset */
 int prl_batch_sync(prl_batch*);

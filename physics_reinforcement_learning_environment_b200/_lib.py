@@ -68,6 +68,7 @@ _SIGNATURES = {
     "prl_batch_rollout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p]),
     "prl_batch_rollout_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_batch_trajectory": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_batch_sync": (C.c_int, [C.c_void_p]),
     "prl_batch_launch_count": (C.c_int64, [C.c_void_p]),
     "prl_ga_create": (C.c_int, [C.c_void_p, C.POINTER(PrlGaConfig), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,

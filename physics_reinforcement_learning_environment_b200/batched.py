@@ -111,6 +111,21 @@ class BatchedEnvironment:
             _ptr(out_step_of_win, np.int32, self.n_envs, "out_step_of_win")))
         return out_score, out_step_of_win
 
+    def trajectory(self, genomes, repeat_move: int, number_of_steps: int):
+        """Replay for the viewers (train.rs:132-159): every genome (a GeneticAgent, main.rs:276-284)
+        is played on a fresh from_world environment for `number_of_steps` steps in one launch.
+        Returns (state[T, n, n_bodies, 9], distance_to_goals[T, n], won[T, n]); the batch's own
+        environments are not touched."""
+        genomes = np.ascontiguousarray(genomes, dtype=np.uint8)
+        n, genome_len = genomes.shape
+        T = int(number_of_steps)
+        state = np.empty((T, n, self.n_bodies, 9), dtype=np.float32)
+        dist = np.empty((T, n), dtype=np.float32)
+        won = np.empty((T, n), dtype=np.uint8)
+        _lib.check(_lib.lib().prl_batch_trajectory(self._h, n, genomes.ctypes.data, genome_len, int(repeat_move), T,
+                                                   state.ctypes.data, dist.ctypes.data, won.ctypes.data))
+        return state, dist, won
+
     def rollout_info(self):
         """(running min distance, step of first win or -1, steps since reset) per environment."""
         s = np.empty(self.n_envs, np.float32)

@@ -367,6 +367,43 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
     return PRL_OK;
 }
 
+int prl_batch_trajectory(prl_batch* b, int64_t n, const uint8_t* genomes, int32_t genome_len, int32_t repeat_move,
+                         int32_t number_of_steps, float* out_state, float* out_distance, uint8_t* out_won) {
+    if (!b || n <= 0 || genome_len < 0 || (genome_len > 0 && !genomes) || repeat_move < 1 || number_of_steps < 0) {
+        set_error("prl_batch_trajectory: bad argument");
+        return PRL_ERR_INVALID;
+    }
+    if (number_of_steps == 0) return PRL_OK;
+    DeviceGuard g(b->device);
+    const int nb = b->host_world.n_bodies;
+    const size_t gbytes = (size_t)n * (size_t)genome_len, recs = (size_t)number_of_steps * (size_t)n;
+    const size_t state_bytes = out_state ? recs * nb * 9 * 4 : 0, dist_bytes = out_distance ? recs * 4 : 0, won_bytes = out_won ? recs : 0;
+    // one scratch allocation for whatever lives on the host: genomes | state | distance | won
+    const bool g_host = gbytes > 0 && !is_device_ptr(genomes);
+    const bool s_host = out_state && !is_device_ptr(out_state), d_host = out_distance && !is_device_ptr(out_distance);
+    const bool w_host = out_won && !is_device_ptr(out_won);
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t off_s = up(g_host ? gbytes : 0), off_d = off_s + up(s_host ? state_bytes : 0), off_w = off_d + up(d_host ? dist_bytes : 0);
+    const size_t total = off_w + up(w_host ? won_bytes : 0);
+    unsigned char* scratch = nullptr;
+    if (total > 0) CUDA_TRY(cudaMalloc((void**)&scratch, total));
+    struct Free { unsigned char* p; ~Free() { if (p) cudaFree(p); } } guard{scratch};
+    const uint8_t* dg = genomes;
+    if (g_host) { CUDA_TRY(cudaMemcpyAsync(scratch, genomes, gbytes, cudaMemcpyHostToDevice, b->stream)); dg = scratch; }
+    float* ds = s_host ? (float*)(scratch + off_s) : out_state;
+    float* dd = d_host ? (float*)(scratch + off_d) : out_distance;
+    uint8_t* dwon = w_host ? (uint8_t*)(scratch + off_w) : out_won;
+    PRL_DISPATCH(pick_variant(b->host_world), trajectory_kernel, grid_for(n), b->stream, b->dev_world, n, dg, genome_len, repeat_move,
+                 number_of_steps, ds, dd, dwon, b->overflow);
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (s_host) CUDA_TRY(cudaMemcpyAsync(out_state, ds, state_bytes, cudaMemcpyDeviceToHost, b->stream));
+    if (d_host) CUDA_TRY(cudaMemcpyAsync(out_distance, dd, dist_bytes, cudaMemcpyDeviceToHost, b->stream));
+    if (w_host) CUDA_TRY(cudaMemcpyAsync(out_won, dwon, won_bytes, cudaMemcpyDeviceToHost, b->stream));
+    if (total > 0) CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return PRL_OK;
+}
+
 int prl_batch_sync(prl_batch* b) {
     if (!b) { set_error("prl_batch_sync: null batch"); return PRL_ERR_INVALID; }
     DeviceGuard g(b->device);

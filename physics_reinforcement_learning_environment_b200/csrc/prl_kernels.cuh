@@ -387,6 +387,56 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     if (out_win) out_win[i] = win_step;
 }
 
+// Replay (train.rs:132-159): n fresh environments each play a GeneticAgent (main.rs:276-284) for
+// number_of_steps steps; every body's state, the distance to the goals and won() are recorded
+// after every step. out_state: steps x n x n_bodies x 9 (layout of gather_state_kernel).
+template <int NB, class WT>
+__global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) trajectory_kernel(const DevWorld* __restrict__ dw, int64_t n,
+                                                                            const uint8_t* __restrict__ genomes, int genome_len,
+                                                                            int repeat_move, int number_of_steps,
+                                                                            float* __restrict__ out_state, float* __restrict__ out_dist,
+                                                                            uint8_t* __restrict__ out_won, int* __restrict__ overflow) {
+    using Sim = SimOf<NB, WT>;
+    __shared__ WT W;
+    __shared__ __align__(16) unsigned char row_pool[(kBlock / 32) * Sim::kWarpBytes + Sim::kPoolPad];
+    stage_world(&W, dw);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    if (!live) i = n - 1;
+    Env<NB> e;
+    Contacts<> ct;
+    env_init(W, e);
+    Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
+    const uint8_t* genome = genomes + i * (int64_t)genome_len;
+    const int nb = W.n_bodies;
+#pragma unroll 1
+    for (int t = 0; t < number_of_steps; ++t) {
+        sim.detect_pending();
+        const int g = t / repeat_move;
+        const uint32_t mv = g < genome_len ? (genome[g] & 7u) : 0u;  // GeneticAgent::get_move
+        const int need = sim.begin_step(mv);
+        float d = 0.0f;
+        solve_in_rounds<Sim>(true, need, [&](int entry, int stride) { d = sim.finish_step(entry, stride); });
+        sim.detect_pending();  // pair removal may wake a body: the recorded state is the state a step kernel would store
+        if (live) {
+            const int64_t rec = (int64_t)t * n + i;
+            if (out_dist) out_dist[rec] = d;
+            if (out_won) out_won[rec] = (e.flags & FLAG_WON) ? 1 : 0;
+            if (out_state) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    if (b < nb) {
+                        float* o = out_state + (rec * nb + b) * 9;
+                        o[0] = e.x[b]; o[1] = e.y[b]; o[2] = e.c[b]; o[3] = e.s[b]; o[4] = e.vx[b]; o[5] = e.vy[b];
+                        o[6] = e.w[b]; o[7] = e.timer[b]; o[8] = (float)((e.sleeping >> b) & 1u);
+                    }
+                }
+            }
+        }
+    }
+    if (live && (e.flags & FLAG_OVERFLOW)) atomicOr(overflow, 1);
+}
+
 // Environment::distance_to_goals (common.rs:175-195) and Environment::won (common.rs:197-199)
 __global__ void __launch_bounds__(kBlock) observe_kernel(const DevWorld* __restrict__ dw, const uint32_t* __restrict__ st, int64_t n,
                                                          float* __restrict__ out_dist, uint8_t* __restrict__ out_won) {

@@ -154,6 +154,24 @@ impl BatchedEnvironment {
         })?;
         Ok(score)
     }
+    /// Replay for the Train-state viewer (train.rs:132-159): the agent's moves are played on a fresh
+    /// environment on the GPU in one launch; returns, per step, every body's
+    /// (x, y, cos, sin, vx, vy, angvel, sleep timer, sleeping), the distance to the goals and won(),
+    /// i.e. what `update_visualization` copies into the sprites frame by frame -- without
+    /// re-simulating on the CPU.
+    pub fn trajectory(&mut self, moves: &[Move], repeat_move: usize, number_of_steps: usize)
+                      -> Result<(Vec<f32>, Vec<f32>, Vec<u8>), PrlError> {
+        let flat: Vec<u8> = moves.iter().map(|m| m.bits()).collect();
+        let nb = unsafe { ffi::prl_batch_num_bodies(self.batch) } as usize;
+        let mut state = vec![0f32; number_of_steps * nb * 9];
+        let mut dist = vec![0f32; number_of_steps];
+        let mut won = vec![0u8; number_of_steps];
+        check(unsafe {
+            ffi::prl_batch_trajectory(self.batch, 1, flat.as_ptr(), flat.len() as i32, repeat_move as i32, number_of_steps as i32,
+                                      state.as_mut_ptr(), dist.as_mut_ptr(), won.as_mut_ptr())
+        })?;
+        Ok((state, dist, won))
+    }
 }
 impl Drop for BatchedEnvironment {
     fn drop(&mut self) {

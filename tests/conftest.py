@@ -69,6 +69,27 @@ def many_supports_world(n_posts=6):
     return {"player_position": [-100.0, 24.0], "objects": objs}
 
 
+def edge_case_worlds():
+    """Levels the editor can produce that the shipped examples do not cover: a block
+    dragged to zero size, the player spawned deep inside a block (parry's penetration path), three
+    goals of which one is rotated and one has a negative scale, and pushable blocks stacked on each
+    other (body-body contacts in a pile) with the player dropped on top."""
+    fixed = lambda x, y, w, h, r=0.0, z=1.0: {"object": {"Block": {"fixed": True}}, "position": [x, y, z], "scale": [w, h], "rotation": r}
+    dyn = lambda x, y, w, h, r=0.0, z=1.0: {"object": {"Block": {"fixed": False}}, "position": [x, y, z], "scale": [w, h], "rotation": r}
+    goal = lambda x, y, w, h, r=0.0, z=9.0: {"object": "Goal", "position": [x, y, z], "scale": [w, h], "rotation": r}
+    return {
+        "zero_size_block": {"player_position": [0.0, 10.0], "objects": [
+            fixed(0.0, -50.0, 800.0, 40.0), fixed(60.0, -25.0, 0.0, 30.0), fixed(-60.0, -30.0, 40.0, 0.0), goal(300.0, 0.0, 80.0, 80.0)]},
+        "deep_penetration": {"player_position": [0.0, 0.0], "objects": [
+            fixed(5.0, -4.0, 200.0, 120.0), fixed(260.0, -80.0, 300.0, 40.0, 0.1), goal(330.0, -20.0, 60.0, 60.0)]},
+        "three_goals": {"player_position": [-50.0, 0.0], "objects": [
+            goal(-300.0, 10.0, 40.0, 40.0, 1.2), fixed(0.0, -50.0, 900.0, 40.0), goal(200.0, 20.0, -60.0, 90.0), goal(60.0, 120.0, 30.0, 30.0, -0.5)]},
+        "stack": {"player_position": [0.0, 160.0], "objects": [
+            fixed(0.0, -50.0, 700.0, 40.0), dyn(0.0, -10.0, 120.0, 40.0), dyn(10.0, 35.0, 90.0, 40.0), dyn(-5.0, 80.0, 60.0, 40.0, 0.1),
+            goal(250.0, 0.0, 70.0, 70.0)]},
+    }
+
+
 def random_genomes(n, genome_len, seed):
     return np.random.Generator(np.random.Philox(seed)).integers(0, 8, size=(n, genome_len), dtype=np.uint8)
 

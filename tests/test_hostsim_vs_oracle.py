@@ -8,7 +8,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ROOT, WORLDS, many_supports_world, n_bodies_of, random_genomes, random_world, synth_world, world_dict
+from conftest import ROOT, WORLDS, edge_case_worlds, many_supports_world, n_bodies_of, random_genomes, random_world, synth_world, world_dict
 from oracle.binding import OracleEnv
 
 _hs = None
@@ -67,6 +67,16 @@ def test_many_constraint_rows(n_posts):
     for g in random_genomes(3, 30, 41 + n_posts):
         t, _, _, _ = host_rollout(world, g, 20, 600, False)
         o = oracle_traj(world, g, 20, 600)
+        assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
+
+
+@pytest.mark.parametrize("name", sorted(edge_case_worlds()))
+def test_editor_edge_cases(name):
+    world = edge_case_worlds()[name]
+    for g in random_genomes(4, 30, 7):
+        t, _, _, _ = host_rollout(world, g, 20, 600, False)
+        o = oracle_traj(world, g, 20, 600)
+        assert np.isfinite(o).all()
         assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
 
 

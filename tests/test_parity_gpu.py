@@ -10,7 +10,7 @@ import pytest
 
 import physics_reinforcement_learning_environment_b200 as prl
 from physics_reinforcement_learning_environment_b200 import _lib
-from conftest import WORLDS, many_supports_world, random_genomes, random_world, synth_world, world_dict, world_text
+from conftest import WORLDS, edge_case_worlds, many_supports_world, random_genomes, random_world, synth_world, world_dict, world_text
 from oracle import binding as oracle
 from oracle.binding import OracleEnv
 
@@ -137,6 +137,26 @@ def test_more_rows_than_a_column_holds_solves_in_rounds(n_posts):
         assert np.array_equal(bits(st[i]), bits(o[i].state()))
 
 
+@pytest.mark.parametrize("name", sorted(edge_case_worlds()))
+def test_editor_edge_cases(name):
+    """Zero-size blocks, a player spawned deep inside a block, several goals, a pile of pushable blocks."""
+    world = edge_case_worlds()[name]
+    n, L, repeat, steps = 160, 30, 20, 600
+    genomes = random_genomes(n, L, 70)
+    env = prl.BatchedEnvironment(prl.World.from_json(json.dumps(world)), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    env.sync()
+    rs, rw, _ = oracle.rollout_batch(world, genomes, repeat, steps, False, n_threads=os.cpu_count())
+    assert np.isfinite(rs).all()
+    assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
+    st = env.state(0, 2)
+    for i in range(2):
+        o = OracleEnv(world)
+        for t in range(steps):
+            o.step(int(genomes[i][t // repeat]))
+        assert np.array_equal(bits(st[i]), bits(o.state()))
+
+
 def test_result_is_independent_of_batch_size_and_neighbours():
     """env i's trajectory must not depend on the batch it sits in (sharding invariance)."""
     genomes = random_genomes(1000, 50, 77)
@@ -191,6 +211,35 @@ def test_reset_and_device_buffers():
     env.distance_to_goals(d)
     torch.cuda.synchronize()
     assert np.array_equal(bits(d.cpu().numpy()), bits(env.distance_to_goals()))
+
+
+@pytest.mark.parametrize("name", WORLDS)
+def test_trajectory_replay_matches_a_cpu_replay(name):
+    """The viewer bridge (train.rs:132-159): a GeneticAgent replayed on a fresh environment, every
+    body recorded after every step -- also past the end of the genome (Move::default()) and past
+    a win (no early exit), with host and device buffers."""
+    import torch
+    world = world_dict(name)
+    n, L, repeat, steps = 5, 12, 20, 300
+    genomes = random_genomes(n, L, 123)
+    genomes[0] = 2
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text(name)), 3)
+    before = env.state()
+    state, dist, won = env.trajectory(genomes, repeat, steps)
+    assert np.array_equal(bits(env.state()), bits(before))  # the batch itself is untouched
+    for i in range(n):
+        agent = prl.GeneticAgent([prl.Move.from_bits(int(b)) for b in genomes[i]], 0, repeat)
+        o = OracleEnv(world)
+        for t in range(steps):
+            o.step(agent.get_move().bits())
+            assert np.array_equal(bits(state[t, i]), bits(o.state())), f"env {i} step {t + 1}"
+            assert bits(dist[t, i]) == bits(np.float32(o.distance_to_goals())) and won[t, i] == o.won()
+    # device buffers
+    dg = torch.from_numpy(genomes).cuda()
+    ds = torch.empty((steps, n, env.n_bodies, 9), dtype=torch.float32, device="cuda")
+    _lib.check(_lib.lib().prl_batch_trajectory(env._h, n, dg.data_ptr(), L, repeat, steps, ds.data_ptr(), None, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(ds.cpu().numpy()), bits(state))
 
 
 def test_goalless_world_reports_no_goal():
