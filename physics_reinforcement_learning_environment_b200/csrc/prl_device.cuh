@@ -63,6 +63,13 @@ PRL_D int warp_max(int v) {
     return v;
 #endif
 }
+PRL_D int popcount(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
 PRL_D int first_bit_from(uint32_t mask, int from) {  // lowest set bit at or above `from`, 32 if none
     uint32_t m = from >= 32 ? 0u : (mask >> from) << from;
 #if defined(__CUDA_ARCH__)
@@ -443,7 +450,7 @@ struct Env {
     int count;
     uint32_t used;       // bit s = slot s is live
     uint64_t spair[2];   // byte s = pair index of slot s (registers: the lists are walked every stage)
-    uint32_t sns;        // 2 bits per slot: number of solver contacts of slot s
+    uint32_t ns1, ns2;   // bit s = slot s has at least one / has two solver contacts
 };
 
 // The contact records of one environment, indexed at run time and therefore in thread-local
@@ -509,6 +516,7 @@ struct Stepper {
     // constraint selection of the current step (begin_step -> finish_step)
     uint32_t active;
     uint64_t cons;      // nibble i = slot of my i-th constraint
+    uint32_t cm_tb, cm_gr;  // slot == pair worlds instead: masks of the two-body / one-body manifolds that become constraints
     int ncons, need, ntb, nplayer;   // constraints, rows, two-body rows (the head of the row list), rows of player pairs
     float im_reg[NB];       // inverse masses (registers: every row update needs one, off the critical path)
     // collision detection owed for the poses of the last position update (detect_pending)
@@ -526,7 +534,7 @@ struct Stepper {
     long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
 #endif
     PRL_D Stepper(const WT& w, E& env, Contacts<S>& contacts, void* warp_pool)
-        : W(w), e(env), k(contacts), pool(static_cast<unsigned char*>(warp_pool)), ent0(0), stride(1), cfm_reg(w.cfm_factor), active(0), cons(0), ncons(0), need(0), ntb(0),
+        : W(w), e(env), k(contacts), pool(static_cast<unsigned char*>(warp_pool)), ent0(0), stride(1), cfm_reg(w.cfm_factor), active(0), cons(0), cm_tb(0), cm_gr(0), ncons(0), need(0), ntb(0),
           nplayer(0), pend_moved(0), pend_all((env.flags & FLAG_FRESH) != 0), first_step(false), gs_n(-1) {
         gs_x[0] = gs_x[1] = gs_y[0] = gs_y[1] = 0.0f;
         gs_b[0] = gs_b[1] = -1;
@@ -563,7 +571,12 @@ struct Stepper {
         for (int it = it_begin(); it_ok(it); it = it_next(it)) ++c;
         return c;
     }
-    PRL_D int ns_of(int slot) const { return (int)((e.sns >> (2 * slot)) & 3u); }
+    PRL_D int ns_of(int slot) const { return (int)(((e.ns1 >> slot) & 1u) + ((e.ns2 >> slot) & 1u)); }
+    PRL_D void set_ns(int slot, int ns) {
+        const uint32_t bit = 1u << slot;
+        e.ns1 = ns >= 1 ? (e.ns1 | bit) : (e.ns1 & ~bit);
+        e.ns2 = ns >= 2 ? (e.ns2 | bit) : (e.ns2 & ~bit);
+    }
     // bodies of pair p's colliders from the packed pair word: -1 for a fixed collider
     PRL_D static int info_b1(uint32_t info) { return (int)(int8_t)((info >> 16) & 0xffu); }
     PRL_D static int info_b2(uint32_t info) { return (int)(int8_t)(info >> 24); }
@@ -628,7 +641,7 @@ struct Stepper {
         }
         f4 a, b, c, d;
         a.x = bits_f32((uint32_t)pair | ((uint32_t)m.npts << 8));
-        e.sns = (e.sns & ~(3u << (2 * slot))) | ((uint32_t)ns << (2 * slot));
+        set_ns(slot, ns);
         if (!kDirect) {
             uint64_t sh = 8 * (slot & 7);
             if (slot < 8) e.spair[0] = (e.spair[0] & ~(0xffull << sh)) | ((uint64_t)pair << sh);
@@ -1106,6 +1119,21 @@ struct Stepper {
         need = 0;
         ntb = 0;
         nplayer = 0;
+        if (kDirect) {
+            // slot == pair: the selection is bit-mask algebra on the live / solver-contact masks and
+            // the world's body -> pairs table; row counts are population counts (ns is 1 or 2)
+            uint32_t awake_pairs = 0;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) if ((active >> b) & 1u) awake_pairs |= W.body_pairs[b];
+            const uint32_t sel_ = e.used & e.ns1 & awake_pairs;
+            cm_tb = sel_ & W.two_body_pairs;
+            cm_gr = sel_ & ~W.two_body_pairs;
+            const uint32_t pl = cm_gr & ((1u << W.n_player_pairs) - 1u);
+            ntb = popcount(cm_tb) + popcount(cm_tb & e.ns2);
+            nplayer = popcount(pl) + popcount(pl & e.ns2);
+            need = popcount(sel_) + popcount(sel_ & e.ns2);
+            return;
+        }
 #pragma unroll 1
         for (int pass = NB == 1 ? 1 : 0; pass < 2; ++pass) {
 #pragma unroll 1
@@ -1137,21 +1165,25 @@ struct Stepper {
         ent0 = first_entry;
         stride = entry_stride;
         int nrows = 0;
-        {
-            // the next manifold's solver contacts are fetched from thread-local memory while the
-            // rows of the current one are built
+        if (kDirect) {
+            // two-body manifolds first, then one-body ("ground") ones, each in ascending pair order
+#pragma unroll 1
+            for (int pass = NB == 1 ? 1 : 0; pass < 2; ++pass) {
+#pragma unroll 1
+                for (uint32_t m_ = pass == 0 ? cm_tb : cm_gr; m_ != 0; m_ &= m_ - 1) {
+                    const int slot = first_bit_from(m_, 0);
+                    const f4 c0 = k.sc[slot][0], c1 = k.sc[slot][1];
+                    nrows = generate_constraint(slot, nrows, c0, c1);
+                }
+            }
+        } else {
             f4 n0 = {}, n1 = {};
             if (ncons > 0) { const int s0_ = (int)(cons & 15u); n0 = k.sc[s0_][0]; n1 = k.sc[s0_][1]; }
 #pragma unroll 1
             for (int i = 0; i < ncons; ++i) {
                 const f4 c0 = n0, c1 = n1;
-#if defined(PRL_SC_PREFETCH)
-                if (i + 1 < ncons) { const int sn = (int)((cons >> (4 * (i + 1))) & 15u); n0 = k.sc[sn][0]; n1 = k.sc[sn][1]; }
-                nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows, c0, c1);
-#else
                 nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows, c0, c1);
                 if (i + 1 < ncons) { const int sn = (int)((cons >> (4 * (i + 1))) & 15u); n0 = k.sc[sn][0]; n1 = k.sc[sn][1]; }
-#endif
             }
         }
         PRL_TICK(5);
@@ -1295,7 +1327,8 @@ struct Stepper {
                     if (b2 >= 0) wake_strong(b2);
                 }
                 e.used &= ~(1u << p);
-                e.sns &= ~(3u << (2 * p));
+                e.ns1 &= ~(1u << p);
+                e.ns2 &= ~(1u << p);
             }
             const uint32_t cand = mod & ov;
             PRL_TICK(0);
@@ -1412,7 +1445,8 @@ struct Stepper {
             store_manifold<SCAN>(p, p, m, pose1);
         } else {
             e.used &= ~(1u << p);
-            e.sns &= ~(3u << (2 * p));
+            e.ns1 &= ~(1u << p);
+            e.ns2 &= ~(1u << p);
         }
     }
     // write a narrow-phase result back at sorted position k; returns the position after it. Only

@@ -83,7 +83,7 @@ __device__ __forceinline__ void stage_world(WT* dst, const DevWorld* __restrict_
     const int t = threadIdx.x, nt = blockDim.x;
     if (t == 0) {
         dst->n_colliders = src->n_colliders; dst->n_bodies = src->n_bodies; dst->n_pairs = src->n_pairs; dst->n_goals = src->n_goals;
-        dst->n_player_pairs = src->n_player_pairs; dst->n_slots = src->n_slots;
+        dst->n_player_pairs = src->n_player_pairs; dst->n_slots = src->n_slots; dst->two_body_pairs = src->two_body_pairs;
         dst->radius = src->radius; dst->half_height = src->half_height; dst->lower_off = src->lower_off;
         dst->dt = src->dt; dst->inv_dt = src->inv_dt; dst->erp_inv_dt = src->erp_inv_dt; dst->cfm_factor = src->cfm_factor;
         dst->prediction = src->prediction; dst->allowed_linear_error = src->allowed_linear_error; dst->aabb_margin = src->aabb_margin;
@@ -130,7 +130,7 @@ __device__ __forceinline__ void env_init(const WT& W, Env<NB>& e) {
     e.count = 0;
     e.used = 0;
     e.spair[0] = e.spair[1] = 0;
-    e.sns = 0;
+    e.ns1 = e.ns2 = 0;
 }
 
 template <int NB, class WT>
@@ -162,7 +162,7 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct
     e.order = 0xfedcba9876543210ull;
     e.used = direct ? 0u : (1u << count) - 1u;
     e.spair[0] = e.spair[1] = 0;
-    e.sns = 0;
+    e.ns1 = e.ns2 = 0;
 #pragma unroll 1
     for (int k = 0; k < count; ++k) {
         int f = base + MF_WORDS * k;

@@ -153,6 +153,7 @@ int build_dev_world(prl_world* w) {
     // colliders never collide
     int np = 0, npp = 0;
     for (int b = 0; b < MAXB; ++b) d.body_pairs[b] = 0;
+    d.two_body_pairs = 0;
     for (int a = 0; a < d.n_colliders; ++a)
         for (int b = a + 1; b < d.n_colliders; ++b) {
             if (d.body_of[a] < 0 && d.body_of[b] < 0) continue;
@@ -161,6 +162,7 @@ int build_dev_world(prl_world* w) {
             d.pair_c2[np] = (uint8_t)b;
             d.pair_info[np] = (uint32_t)a | ((uint32_t)b << 8) | ((uint32_t)(d.body_of[a] & 0xff) << 16) | ((uint32_t)(d.body_of[b] & 0xff) << 24);
             if (np < 32) {
+                if (d.body_of[a] >= 0 && d.body_of[b] >= 0) d.two_body_pairs |= 1u << np;
                 if (d.body_of[a] >= 0) d.body_pairs[d.body_of[a]] |= 1u << np;
                 if (d.body_of[b] >= 0) d.body_pairs[d.body_of[b]] |= 1u << np;
             }

@@ -28,6 +28,7 @@ struct alignas(16) DevWorldT {
     int32_t n_colliders, n_bodies, n_pairs, n_goals;
     int32_t n_player_pairs;  // pairs whose collider1 is the player capsule come first
     int32_t n_slots;         // manifold slots kept per environment in HBM = min(n_pairs, MAXC)
+    uint32_t two_body_pairs; // bit p = both colliders of candidate pair p belong to bodies (first 32 pairs)
     // player capsule (common.rs:74-86) and glue constants (common.rs:216-220, 234-236)
     float radius, half_height, lower_off;
     // integration parameters (rapier IntegrationParameters::default, derived values)

@@ -94,7 +94,7 @@ template <class WT>
 static void copy_world(WT& d, const DevWorld& s) {
     memset(&d, 0, sizeof d);
     d.n_colliders = s.n_colliders; d.n_bodies = s.n_bodies; d.n_pairs = s.n_pairs; d.n_goals = s.n_goals;
-    d.n_player_pairs = s.n_player_pairs; d.n_slots = s.n_slots;
+    d.n_player_pairs = s.n_player_pairs; d.n_slots = s.n_slots; d.two_body_pairs = s.two_body_pairs;
     d.radius = s.radius; d.half_height = s.half_height; d.lower_off = s.lower_off;
     d.dt = s.dt; d.inv_dt = s.inv_dt; d.erp_inv_dt = s.erp_inv_dt; d.cfm_factor = s.cfm_factor;
     d.prediction = s.prediction; d.allowed_linear_error = s.allowed_linear_error; d.aabb_margin = s.aabb_margin; d.scale = s.scale;
