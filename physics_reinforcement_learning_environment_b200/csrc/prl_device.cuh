@@ -498,7 +498,7 @@ struct Stepper {
     // stride = 32 / G and ent0 = the lane's column, so the lanes of a round always touch
     // consecutive entries. G == 1 in all but a fraction of a percent of the steps.
     static constexpr int kCap = CAP;
-    static_assert(CAP >= 4 && CAP <= 8, "column height");
+    static_assert(CAP >= 4 && CAP <= 10, "column height");
     static constexpr int kEntries = 32 * CAP;   // entries per plane per warp
     static constexpr int kRowBytes = 48 + (NB > 2 ? 8 : 0);
     static constexpr int kWarpBytes = kEntries * kRowBytes;

@@ -24,14 +24,17 @@ namespace prl {
 constexpr int kBlock = 64;
 constexpr int kWarpBlock = 32;  // rollouts of populations too small to fill the SMs with 64-thread blocks
 // Shared memory of a block: the world tables plus, per warp, the planes of velocity-constraint
-// rows (prl_device.cuh, Stepper): 32 columns of RowCap rows. Single-body worlds rarely need more
-// than two rows per environment and get 4-row columns (6 KB per warp). push.json needs 6 or 7 rows
-// in most steps and 8 or 9 in 0.3 % of them: 7-row columns (10.5 KB per warp) keep a 448-thread
-// block under 164 KB of shared memory, which leaves the SM 92 KB of L1 for the manifold records
-// in thread-local memory (8-row columns: 60 KB). More than one pushable block: 8-row columns.
-// A 65536-environment batch puts 7 64-thread blocks (or one 448-thread block) on each SM.
+// rows (prl_device.cuh, Stepper): 32 columns of RowCap rows. Single-body worlds need at most three
+// rows per environment and get 4-row columns (6 KB per warp). With pushable blocks the column must
+// hold EVERY row an environment can reasonably need: a warp with one lane over the limit solves in
+// rounds, i.e. takes twice as long, and the block's other 13 warps wait for it at the step barrier
+// (push.json needs 8 or 9 rows in only 0.2 % of the environment steps, yet with 7-row columns 63 % of
+// the steps had such a lane somewhere in the block: 9-row columns were 27 % faster than 7-row ones).
+// One pushable block: 10-row columns (15 KB per warp, 215 KB per 448-thread block); more: 8-row
+// columns of 56-byte rows (all that fits). A 65536-environment batch puts 7 64-thread blocks (or
+// one 448-thread block) on each SM.
 #ifndef PRL_ROWCAP2
-#define PRL_ROWCAP2 7
+#define PRL_ROWCAP2 10
 #endif
 template <int NB> struct RowCap { static constexpr int value = NB == 1 ? 4 : (NB == 2 ? PRL_ROWCAP2 : 8); };
 template <int NB, class WT> using SimOf = Stepper<NB, MAXC, WT, RowCap<NB>::value>;
