@@ -334,7 +334,7 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
         cudaError_t le = cudaSuccess;
 #define PRL_ROLLOUT(NB_, WT_, BLOCK_)                                                                                     \
     do {                                                                                                                  \
-        const size_t smem = rollout_smem_bytes<NB_, WT_>(BLOCK_);                                                         \
+        const size_t smem = rollout_smem_bytes<NB_, WT_, BLOCK_>();                                                         \
         static unsigned long long configured = 0; /* function attributes are per device */                                \
         const unsigned long long dev_bit = 1ull << (b->device & 63);                                                      \
         if (!(configured & dev_bit)) {                                                                                    \

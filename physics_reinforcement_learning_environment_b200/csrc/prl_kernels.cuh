@@ -36,26 +36,31 @@ constexpr int kWarpBlock = 32;  // rollouts of populations too small to fill the
 #ifndef PRL_ROWCAP2
 #define PRL_ROWCAP2 10
 #endif
-template <int NB> struct RowCap { static constexpr int value = NB == 1 ? 4 : (NB == 2 ? PRL_ROWCAP2 : 8); };
-template <int NB, class WT> using SimOf = Stepper<NB, MAXC, WT, RowCap<NB>::value>;
+// (kernels of 64- and 32-thread blocks have no block barrier, so a round only costs the warp that
+// needs it: they keep 7-row columns, which lets seven 64-thread blocks share an SM)
+template <int NB, int BLOCK> struct RowCap { static constexpr int value = NB == 1 ? 4 : (NB == 2 ? (BLOCK > 64 ? PRL_ROWCAP2 : 7) : 8); };
+template <int NB, class WT, int BLOCK = 64> using SimOf = Stepper<NB, MAXC, WT, RowCap<NB, BLOCK>::value>;
 // Rollouts of large batches run ONE block of 448 threads per SM (the same 14 warps, 148 x 448 >=
 // 65536) with a block barrier at the top of every step: the step is ~4000 straight-line
 // instructions outside the solver's loops, and warps of one SM that are in the same phase of the
 // step share their instruction fetches (measured +19 % over 7 independent 64-thread blocks, whose
 // top stall was no_instruction). Small batches keep 64-thread blocks so they spread over the SMs.
 constexpr int kBigBlock = 448;
-// Every kRegroupEvery steps a 448-thread block re-deals its environments to its threads, sorted
+// Every kRegroupEvery steps (measured: 32: -1.7 %, 64: -0.5 %, 128 and 256 equal) a 448-thread block re-deals its environments to its threads, sorted
 // by how many solver rows they needed last step (finished rollouts last): environments parked in
 // the HBM state arrays, a counting sort in shared memory, and each thread picks up its new
 // environment. Warps then hold environments of similar cost, so fewer lanes idle while their
 // neighbours solve contacts (and warps of finished rollouts only hit the barrier).
-constexpr int kRegroupEvery = 64;
+#ifndef PRL_REGROUP_EVERY
+#define PRL_REGROUP_EVERY 128
+#endif
+constexpr int kRegroupEvery = PRL_REGROUP_EVERY;
 constexpr int kRegroupKeys = 34;  // 0 = finished, 1 + min(rows, 32)
 constexpr size_t kRegroupBytes = (kRegroupKeys + 2 * kBigBlock) * sizeof(int);
-template <int NB, class WT>
-constexpr size_t rollout_smem_bytes(int block) {
-    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(block / 32) * SimOf<NB, WT>::kWarpBytes + SimOf<NB, WT>::kPoolPad +
-           (block == kBigBlock ? kRegroupBytes : 0);
+template <int NB, class WT, int BLOCK>
+constexpr size_t rollout_smem_bytes() {
+    return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(BLOCK / 32) * SimOf<NB, WT, BLOCK>::kWarpBytes + SimOf<NB, WT, BLOCK>::kPoolPad +
+           (BLOCK == kBigBlock ? kRegroupBytes : 0);
 }
 
 // One step's solve for the lanes of a warp. The warp first agrees on the shape of its row
@@ -284,7 +289,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
                                                          int number_of_steps, int early_exit,
                                                          float* __restrict__ out_score, int32_t* __restrict__ out_win,
                                                          int* __restrict__ overflow) {
-    using Sim = SimOf<NB, WT>;
+    using Sim = SimOf<NB, WT, BLOCK>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WT& W = *reinterpret_cast<WT*>(smem_raw);
     unsigned char* row_pool = smem_raw + ((sizeof(WT) + 15) / 16) * 16;
