@@ -171,16 +171,23 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct
     e.used = direct ? 0u : (1u << count) - 1u;
     e.spair[0] = e.spair[1] = 0;
     e.ns1 = e.ns2 = 0;
-#pragma unroll 1
+    // all 15 words of a slot are requested before the first one is used, and two slots per trip:
+    // this loop is a chain of global-memory latencies, not of bytes
+#pragma unroll 2
     for (int k = 0; k < count; ++k) {
         int f = base + MF_WORDS * k;
-        uint32_t h = st[(int64_t)f * n + i];
+        uint32_t w[MF_WORDS];
+#pragma unroll
+        for (int j = 0; j < MF_WORDS; ++j) w[j] = st[(int64_t)(f + j) * n + i];
+        const uint32_t h = w[0];
         int slot = direct ? (int)(h & 0xffu) : k;
         if (direct) e.used |= 1u << slot;
-        float* rec = &ct.mf[slot][0].x;
-        rec[0] = __uint_as_float(h);
-#pragma unroll 1
-        for (int j = 1; j < MF_WORDS; ++j) rec[j] = ld(f + j);
+        f4* rec = ct.mf[slot];
+        f4 q;
+        q.x = __uint_as_float(w[0]); q.y = __uint_as_float(w[1]); q.z = __uint_as_float(w[2]); q.w = __uint_as_float(w[3]); rec[0] = q;
+        q.x = __uint_as_float(w[4]); q.y = __uint_as_float(w[5]); q.z = __uint_as_float(w[6]); q.w = __uint_as_float(w[7]); rec[1] = q;
+        q.x = __uint_as_float(w[8]); q.y = __uint_as_float(w[9]); q.z = __uint_as_float(w[10]); q.w = __uint_as_float(w[11]); rec[2] = q;
+        q.x = __uint_as_float(w[12]); q.y = __uint_as_float(w[13]); q.z = __uint_as_float(w[14]); q.w = 0.0f; rec[3] = q;
     }
 }
 
@@ -208,10 +215,13 @@ __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, const C
         int slot = direct ? __ffs((int)left) - 1 : (int)((e.order >> (4 * k)) & 15u);
         left &= left - 1;
         int f = base + MF_WORDS * k;
-        const float* rec = &ct.mf[slot][0].x;
-        st[(int64_t)f * n + i] = __float_as_uint(rec[0]) & 0xfffu;  // pair | npts << 8 (solver-contact count is derived)
-#pragma unroll 1
-        for (int j = 1; j < MF_WORDS; ++j) sf(f + j, rec[j]);
+        const f4* rec = ct.mf[slot];
+        const f4 a = rec[0], b = rec[1], c = rec[2], d = rec[3];
+        st[(int64_t)f * n + i] = __float_as_uint(a.x) & 0xfffu;  // pair | npts << 8 (solver-contact count is derived)
+        sf(f + 1, a.y); sf(f + 2, a.z); sf(f + 3, a.w);
+        sf(f + 4, b.x); sf(f + 5, b.y); sf(f + 6, b.z); sf(f + 7, b.w);
+        sf(f + 8, c.x); sf(f + 9, c.y); sf(f + 10, c.z); sf(f + 11, c.w);
+        sf(f + 12, d.x); sf(f + 13, d.y); sf(f + 14, d.z);
     }
 }
 
