@@ -19,17 +19,22 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle.binding import OracleEnv  # noqa: E402
+from conftest import edge_case_worlds, many_supports_world  # noqa: E402
 
 
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
-    for name in ("right", "jump", "push"):
-        world = json.load(open(os.path.join(ROOT, "worlds", f"{name}.json")))
+    worlds = {name: json.load(open(os.path.join(ROOT, "worlds", f"{name}.json"))) for name in ("right", "jump", "push")}
+    # levels the editor can produce that the shipped examples do not cover; their JSON travels in the fixture
+    worlds.update({f"edge_{k}": v for k, v in edge_case_worlds().items()})
+    worlds["edge_many_supports"] = many_supports_world(6)
+    for name, world in worlds.items():
         rng = np.random.Generator(np.random.Philox(0xB200))
         genomes = rng.integers(0, 8, size=(16, 50), dtype=np.uint8)
         genomes[:8] = np.arange(8, dtype=np.uint8)[:, None]  # the 8 constant moves of README.md:96-114
-        repeat, steps = 20, 1000
+        repeat, steps = 20, (1000 if not name.startswith("edge_") else 400)
         env = OracleEnv(world)
         score = np.zeros(16, np.float32); win = np.zeros(16, np.int32); run = np.zeros(16, np.int32)
         for i in range(16):
@@ -40,7 +45,7 @@ def main():
             for t in range(steps):
                 env.step(int(genomes[g][t // repeat]))
                 traj[gi, t] = env.state()
-        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), genomes=genomes, repeat_move=repeat,
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), world_json=np.array(json.dumps(world)), genomes=genomes, repeat_move=repeat,
                             number_of_steps=steps, score=score, step_of_win=win, steps_run=run,
                             traj_genomes=np.array((2, 6, 8, 9)), traj=traj[:, ::10].copy())
         print(name, "scores", score[:8], "wins", win)
