@@ -553,9 +553,9 @@ struct Stepper {
     PRL_D float& acc_t(int en) const { return reinterpret_cast<float*>(pool + kOff4)[en]; }
     PRL_D f2& q5(int en) const { return reinterpret_cast<f2*>(pool + kOff5)[en]; }
 
-    // slot == pair index. (Single-body worlds measured 7 % faster with the sorted list: they rarely
-    // hold more than two manifolds.)
-    static constexpr bool kDirect = WT::kMaxPairs <= S && NB > 1;
+    // slot == pair index for worlds with at most S candidate pairs (the shipped levels): the live
+    // manifolds are a bit mask, and selection / broad phase are mask algebra
+    static constexpr bool kDirect = WT::kMaxPairs <= S;
     PRL_D int slot_at(int k) const { return (int)((e.order >> (4 * k)) & 15u); }
     PRL_D int pair_of(int slot) const {
         return kDirect ? slot : (int)(((slot < 8 ? e.spair[0] : e.spair[1]) >> (8 * (slot & 7))) & 0xffu);
@@ -1373,8 +1373,7 @@ struct Stepper {
         int ncand = 0;
         {
             int k = 0;  // position in the sorted manifold list of the first entry with pair >= p
-#pragma unroll 1
-            for (int p = 0; p < W.n_pairs; ++p) {
+            auto visit = [&](int p) {
                 bool modified;
                 bool ov = pair_overlaps(p, moved, all, bmnx, bmny, bmxx, bmxy, modified);
                 bool have = k < e.count && pair_at(k) == p;
@@ -1397,6 +1396,32 @@ struct Stepper {
                     }
                     else e.flags |= FLAG_OVERFLOW;
                 }
+            };
+            if (NB == 1 && W.grid_n > 0) {
+                // single-body world: every pair is (player, fixed collider). Only the pairs the x grid
+                // lists for the player's cells can overlap; the pairs of the live manifolds are
+                // visited too (one that no longer overlaps drops its manifold), all in pair order.
+                uint32_t vm[4] = {0u, 0u, 0u, 0u};
+                const int c0 = grid_cell(W, bmnx[0]), c1 = grid_cell(W, bmxx[0]);
+#pragma unroll 1
+                for (int c = c0; c <= c1; ++c) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) vm[q] |= W.grid_mask[c][q];
+                }
+#pragma unroll 1
+                for (int j = 0; j < e.count; ++j) {
+                    const int p = pair_at(j);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) if ((p >> 5) == q) vm[q] |= 1u << (p & 31);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+#pragma unroll 1
+                    for (uint32_t m_ = vm[q]; m_ != 0; m_ &= m_ - 1) visit(32 * q + first_bit_from(m_, 0));
+                }
+            } else {
+#pragma unroll 1
+                for (int p = 0; p < W.n_pairs; ++p) visit(p);
             }
         }
         // Narrow phase on "my i-th candidate": the lanes of a warp work on different pairs in

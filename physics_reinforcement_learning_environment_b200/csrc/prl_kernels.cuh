@@ -96,7 +96,10 @@ __device__ __forceinline__ void stage_world(WT* dst, const DevWorld* __restrict_
         dst->dt = src->dt; dst->inv_dt = src->inv_dt; dst->erp_inv_dt = src->erp_inv_dt; dst->cfm_factor = src->cfm_factor;
         dst->prediction = src->prediction; dst->allowed_linear_error = src->allowed_linear_error; dst->aabb_margin = src->aabb_margin;
         dst->scale = src->scale;
+        dst->grid_n = WT::kGrid > 1 ? src->grid_n : 0; dst->grid_x0 = src->grid_x0; dst->grid_inv_w = src->grid_inv_w;
     }
+    if (WT::kGrid > 1)
+        for (int c = t; c < WT::kGrid * 4; c += nt) dst->grid_mask[c >> 2][c & 3] = src->grid_mask[c >> 2][c & 3];
     for (int c = t; c < src->n_colliders; c += nt) {
         dst->cx[c] = src->cx[c]; dst->cy[c] = src->cy[c]; dst->cc[c] = src->cc[c]; dst->cs[c] = src->cs[c];
         dst->hx[c] = src->hx[c]; dst->hy[c] = src->hy[c];

@@ -180,6 +180,26 @@ int build_dev_world(prl_world* w) {
         }
     d.n_pairs = np;
     d.n_player_pairs = npp;
+    // x grid over the player's pairs with a fixed collider (used by single-body worlds)
+    d.grid_n = 0;
+    d.grid_x0 = 0.0f;
+    d.grid_inv_w = 0.0f;
+    for (int c = 0; c < DevWorld::kGrid; ++c) for (int q = 0; q < 4; ++q) d.grid_mask[c][q] = 0;
+    if (d.n_bodies == 1 && np > 0) {
+        float lo = 3.0e38f, hi = -3.0e38f;
+        for (int p = 0; p < np; ++p) { lo = fminf(lo, d.pair_box[p][0]); hi = fmaxf(hi, d.pair_box[p][2]); }
+        const int gn = DevWorld::kGrid;
+        const float w = (hi - lo) / (float)gn;
+        if (w > 0.0f && w < 3.0e38f) {
+            d.grid_n = gn;
+            d.grid_x0 = lo;
+            d.grid_inv_w = 1.0f / w;
+            for (int p = 0; p < np; ++p) {
+                const int c0 = grid_cell(d, d.pair_box[p][0]), c1 = grid_cell(d, d.pair_box[p][2]);
+                for (int c = c0; c <= c1; ++c) d.grid_mask[c][p >> 5] |= 1u << (p & 31);
+            }
+        }
+    }
     d.n_slots = np < MAXC ? np : MAXC;
     return PRL_OK;
 }

@@ -6,6 +6,7 @@
 // `IntegrationParameters::default()` (common.rs:89). It is identical for every environment of a
 // batch, lives once in HBM and is staged into shared memory by every thread block.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/prl.h"
@@ -55,12 +56,31 @@ struct alignas(16) DevWorldT {
     alignas(16) float pair_box[MP][4];
     alignas(16) float pair_pose[MP][4];
     alignas(16) float pair_he[MP][4];
+    // x grid over the fixed colliders of the player's pairs (worlds too large for slot == pair
+    // manifolds): grid_mask[c] = pairs whose fixed collider's loosened AABB reaches cell c, cells
+    // c = clamp(floor((x - grid_x0) * grid_inv_w), 0, grid_n - 1), the end cells open-ended. The
+    // broad phase of a single-body world then tests a handful of pairs instead of all of them.
+    static constexpr int kGrid = MP > 32 ? 64 : 1;
+    int32_t grid_n;
+    float grid_x0, grid_inv_w;
+    uint32_t grid_mask[kGrid][4];
     // goals (common.rs:148-157, 175-195)
     float gx[MG], gy[MG], ghw[MG], ghh[MG];        // centre, width/2, height/2
     float gxax[MG], gxay[MG], gyax[MG], gyay[MG];  // Quat::from_rotation_z(rot) * X / Y, truncated
 };
 using DevWorld = DevWorldT<MAXCOL, MAXP, MAXG>;
 using DevWorldSmall = DevWorldT<16, MAXC, 4>;  // <= MAXC pairs: manifold slot == pair index (Stepper::kDirect)
+
+// cell of x in the world's x grid; monotone in x, identical on host and device (plain f32 ops)
+template <class WT>
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int grid_cell(const WT& w, float x) {
+    float f = floorf((x - w.grid_x0) * w.grid_inv_w);
+    int c = f < 0.0f ? 0 : (f > (float)(w.grid_n - 1) ? w.grid_n - 1 : (int)f);
+    return c;
+}
 
 template <class WT>
 inline bool world_fits(const DevWorld& w) {

@@ -98,6 +98,8 @@ static void copy_world(WT& d, const DevWorld& s) {
     d.radius = s.radius; d.half_height = s.half_height; d.lower_off = s.lower_off;
     d.dt = s.dt; d.inv_dt = s.inv_dt; d.erp_inv_dt = s.erp_inv_dt; d.cfm_factor = s.cfm_factor;
     d.prediction = s.prediction; d.allowed_linear_error = s.allowed_linear_error; d.aabb_margin = s.aabb_margin; d.scale = s.scale;
+    d.grid_n = WT::kGrid > 1 ? s.grid_n : 0; d.grid_x0 = s.grid_x0; d.grid_inv_w = s.grid_inv_w;
+    if (WT::kGrid > 1) for (int c = 0; c < WT::kGrid; ++c) for (int q = 0; q < 4; ++q) d.grid_mask[c][q] = s.grid_mask[c][q];
     for (int c = 0; c < s.n_colliders; ++c) {
         d.cx[c] = s.cx[c]; d.cy[c] = s.cy[c]; d.cc[c] = s.cc[c]; d.cs[c] = s.cs[c]; d.hx[c] = s.hx[c]; d.hy[c] = s.hy[c];
         d.amnx[c] = s.amnx[c]; d.amny[c] = s.amny[c]; d.amxx[c] = s.amxx[c]; d.amxy[c] = s.amxy[c]; d.body_of[c] = s.body_of[c];
