@@ -43,17 +43,18 @@ inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBloc
 // Kernel variants: (bodies, world-table capacity). Small worlds (<= 15 blocks, the shipped
 // levels) with at most one pushable block get the compact tables and the 48-byte solver rows;
 // everything else runs the general variant.
-enum Variant { V1_SMALL, V2_SMALL, V1_BIG, VN_BIG };
+enum Variant { V1_SMALL, V2_SMALL, VN_SMALL, V1_BIG, VN_BIG };
 Variant pick_variant(const DevWorld& w) {
     bool small = world_fits<DevWorldSmall>(w);
     if (w.n_bodies == 1) return small ? V1_SMALL : V1_BIG;
-    if (w.n_bodies == 2 && small) return V2_SMALL;
+    if (small) return w.n_bodies == 2 ? V2_SMALL : VN_SMALL;
     return VN_BIG;
 }
 #define PRL_DISPATCH(variant, KERNEL, grid, stream, ...)                                                        \
     switch (variant) {                                                                                           \
         case V1_SMALL: KERNEL<1, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;               \
         case V2_SMALL: KERNEL<2, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;               \
+        case VN_SMALL: KERNEL<MAXB, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;            \
         case V1_BIG: KERNEL<1, DevWorld><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;                      \
         default: KERNEL<MAXB, DevWorld><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;                       \
     }
@@ -352,6 +353,7 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
                 else if (tiny) PRL_ROLLOUT(2, DevWorldSmall, kWarpBlock);
                 else PRL_ROLLOUT(2, DevWorldSmall, kBlock);
                 break;
+            case VN_SMALL: if (big) PRL_ROLLOUT(MAXB, DevWorldSmall, kBigBlock); else PRL_ROLLOUT(MAXB, DevWorldSmall, kBlock); break;
             case V1_BIG: if (tiny) PRL_ROLLOUT(1, DevWorld, kWarpBlock); else PRL_ROLLOUT(1, DevWorld, kBlock); break;
             default: if (big) PRL_ROLLOUT(MAXB, DevWorld, kBigBlock); else PRL_ROLLOUT(MAXB, DevWorld, kBlock); break;
         }
