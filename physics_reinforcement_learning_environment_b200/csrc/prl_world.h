@@ -78,8 +78,8 @@ __host__ __device__
 #endif
 inline int grid_cell(const WT& w, float x) {
     float f = floorf((x - w.grid_x0) * w.grid_inv_w);
-    int c = f < 0.0f ? 0 : (f > (float)(w.grid_n - 1) ? w.grid_n - 1 : (int)f);
-    return c;
+    if (!(f >= 0.0f)) return 0;  // left of the grid (or NaN)
+    return f > (float)(w.grid_n - 1) ? w.grid_n - 1 : (int)f;
 }
 
 template <class WT>
