@@ -174,9 +174,9 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct
     e.used = direct ? 0u : (1u << count) - 1u;
     e.spair[0] = e.spair[1] = 0;
     e.ns1 = e.ns2 = 0;
-    // all 15 words of a slot are requested before the first one is used, and two slots per trip:
+    // all 15 words of a slot are requested before the first one is used:
     // this loop is a chain of global-memory latencies, not of bytes
-#pragma unroll 2
+#pragma unroll 1
     for (int k = 0; k < count; ++k) {
         int f = base + MF_WORDS * k;
         uint32_t w[MF_WORDS];
