@@ -35,6 +35,8 @@
 #define PRL_D inline
 #define PRL_COLD static inline
 #endif
+// rarely taken branches: laid out away from the hot path (the step is instruction-fetch sensitive)
+#define PRL_UNLIKELY(x) __builtin_expect(!!(x), 0)
 
 // PRL_PHASE_TIMING (profiling builds only, never the product): per-warp cycle counts of the phases
 // of a step, printed by block 0 of the rollout kernel
@@ -713,7 +715,7 @@ struct Stepper {
     // common.rs:216-313: ground-contact scan over the player's contact pairs, then the move
     // impulses. The scan normally comes from the narrow phase (gs_*, see store_manifold).
     PRL_D void player_move(uint32_t mv) {
-        if (gs_n < 0 || gs_n > 2) { player_move_stored(mv); return; }
+        if (PRL_UNLIKELY(gs_n < 0 || gs_n > 2)) { player_move_stored(mv); return; }
         const int nfc = gs_n;
         if (nfc == 0) return;
         v2 lower = V(e.x[0], e.y[0] - W.lower_off);

@@ -72,7 +72,7 @@ template <class SIM, class F>
 __device__ __forceinline__ void solve_in_rounds(bool run, int need, F&& body) {
     const int mx = warp_max(need);
     const int lane = (int)(threadIdx.x & 31u);
-    if (mx <= SIM::kCap) {
+    if (!PRL_UNLIKELY(mx > SIM::kCap)) {
         if (run) body(lane, 32);
         return;
     }
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
         const bool all_done = __syncthreads_and(!(t < total));
         PRL_TICK_K(8);
         if (all_done) break;
-        if (BLOCK == kBigBlock && iter > 0 && iter % kRegroupEvery == 0) {
+        if (BLOCK == kBigBlock && PRL_UNLIKELY(iter > 0 && iter % kRegroupEvery == 0)) {
             // ---- regroup: park, sort, pick up (all threads of the block are here, nothing pending)
             int* hist = regroup;
             int* perm_env = regroup + kRegroupKeys;
