@@ -611,8 +611,9 @@ struct Stepper {
     // store a manifold with points and refresh its solver contacts (rapier
     // NarrowPhase::compute_contacts tail: points with dist < prediction, at the midpoint between
     // the two surfaces, in world space)
+    // scan: the pair is one of the player's -- its floor contacts feed the ground-contact scan
     template <bool SCAN = false>
-    PRL_D void store_manifold(int slot, int pair, const Manifold& m, const Iso& pose1) {
+    PRL_D void store_manifold(int slot, int pair, const Manifold& m, const Iso& pose1, bool scan = SCAN) {
         v2 normal = rot(pose1.c, pose1.s, m.n1);
         int ns = 0;
         float px[2] = {0.0f, 0.0f}, py[2] = {0.0f, 0.0f}, pd[2] = {0.0f, 0.0f};
@@ -627,7 +628,7 @@ struct Stepper {
                 ++ns;
             }
         }
-        if (SCAN && gs_n >= 0) {  // a player pair: floor contacts among its solver contacts (common.rs:234-238)
+        if (scan && gs_n >= 0) {  // a player pair: floor contacts among its solver contacts (common.rs:234-238)
             const int body = info_b2(W.pair_info[pair]);
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
@@ -1334,34 +1335,32 @@ struct Stepper {
             }
             const uint32_t cand = mod & ov;
             PRL_TICK(0);
-            // narrow phase on "my i-th candidate": player pairs (capsule-cuboid) first, then block pairs
-            const uint32_t pmask = (1u << W.n_player_pairs) - 1u;
+            // Narrow phase on "my i-th candidate", player pairs and block pairs in ONE loop: what runs
+            // almost always -- manifold persistence, solver contacts, the store -- is the same code
+            // for both, only the out-of-line recompute differs. (Two loops doubled the hot code and
+            // ran max(player pairs) + max(block pairs) trips per warp instead of max(pairs).)
+            const int npp = W.n_player_pairs;
 #pragma unroll 1
-            for (uint32_t m_ = cand & pmask; m_ != 0; m_ &= m_ - 1) {
-                int p = first_bit_from(m_, 0);
+            for (uint32_t m_ = cand; m_ != 0; m_ &= m_ - 1) {
+                const int p = first_bit_from(m_, 0);
+                const uint32_t info = W.pair_info[p];
                 const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
                 Manifold m;
                 if (e.used & (1u << p)) load_manifold(p, m);
                 else m.npts = 0;
-                Iso pose1 = body_pose(0);
-                Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(W.pair_info[p])));
-                contact_capsule_cuboid(m, pos12, W.radius, W.half_height, V(he.z, he.w), W.prediction);
-                commit_direct<true>(p, m, pose1);
-            }
-            PRL_TICK(1);
-            if (NB > 1) {
-#pragma unroll 1
-                for (uint32_t m_ = cand & ~pmask; m_ != 0; m_ &= m_ - 1) {
-                    int p = first_bit_from(m_, 0);
-                    const uint32_t info = W.pair_info[p];
-                    const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
-                    Manifold m;
-                    if (e.used & (1u << p)) load_manifold(p, m);
-                    else m.npts = 0;
-                    Iso pose1 = pair_collider_pose(p, info_b1(info));
-                    Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(info)));
-                    contact_cuboid_cuboid(m, pos12, V(he.x, he.y), V(he.z, he.w), W.prediction);
-                    commit_direct(p, m, pose1);
+                const Iso pose1 = pair_collider_pose(p, info_b1(info));
+                const Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(info)));
+                if (!manifold_try_update(m, pos12)) {
+                    if (NB == 1 || p < npp) m = contact_capsule_cuboid_full(pos12, W.radius, W.half_height, V(he.z, he.w), W.prediction);
+                    else m = contact_cuboid_cuboid_full(pos12, V(he.x, he.y), V(he.z, he.w), W.prediction);
+                }
+                if (m.npts > 0) {
+                    e.used |= 1u << p;
+                    store_manifold(p, p, m, pose1, NB == 1 || p < npp);
+                } else {
+                    e.used &= ~(1u << p);
+                    e.ns1 &= ~(1u << p);
+                    e.ns2 &= ~(1u << p);
                 }
             }
             PRL_TICK(2);
