@@ -1464,17 +1464,6 @@ struct Stepper {
             }
         }
     }
-    template <bool SCAN = false>
-    PRL_D void commit_direct(int p, const Manifold& m, const Iso& pose1) {
-        if (m.npts > 0) {
-            e.used |= 1u << p;
-            store_manifold<SCAN>(p, p, m, pose1);
-        } else {
-            e.used &= ~(1u << p);
-            e.ns1 &= ~(1u << p);
-            e.ns2 &= ~(1u << p);
-        }
-    }
     // write a narrow-phase result back at sorted position k; returns the position after it. Only
     // manifolds with points are kept: an empty one carries no state the next step can observe.
     template <bool SCAN = false>
