@@ -1169,15 +1169,17 @@ struct Stepper {
         stride = entry_stride;
         int nrows = 0;
         if (kDirect) {
-            // two-body manifolds first, then one-body ("ground") ones, each in ascending pair order
+            // two-body manifolds first, then one-body ("ground") ones, each in ascending pair order --
+            // as ONE sequence per lane, so that a warp runs max(constraints) trips, not
+            // max(two-body) + max(ground): nearly every warp has a lane whose player stands on the block
+            uint32_t mt = NB > 1 ? cm_tb : 0u, mg = cm_gr;
 #pragma unroll 1
-            for (int pass = NB == 1 ? 1 : 0; pass < 2; ++pass) {
-#pragma unroll 1
-                for (uint32_t m_ = pass == 0 ? cm_tb : cm_gr; m_ != 0; m_ &= m_ - 1) {
-                    const int slot = first_bit_from(m_, 0);
-                    const f4 c0 = k.sc[slot][0], c1 = k.sc[slot][1];
-                    nrows = generate_constraint(slot, nrows, c0, c1);
-                }
+            while ((mt | mg) != 0) {
+                const uint32_t cur = mt != 0 ? mt : mg;
+                const int slot = first_bit_from(cur, 0);
+                if (mt != 0) mt &= mt - 1; else mg &= mg - 1;
+                const f4 c0 = k.sc[slot][0], c1 = k.sc[slot][1];
+                nrows = generate_constraint(slot, nrows, c0, c1);
             }
         } else {
             f4 n0 = {}, n1 = {};
