@@ -30,11 +30,12 @@ constexpr int kWarpBlock = 32;  // rollouts of populations too small to fill the
 // rounds, i.e. takes twice as long, and the block's other 13 warps wait for it at the step barrier
 // (push.json needs 8 or 9 rows in only 0.2 % of the environment steps, yet with 7-row columns 63 % of
 // the steps had such a lane somewhere in the block: 9-row columns were 27 % faster than 7-row ones).
-// One pushable block: 10-row columns (15 KB per warp, 215 KB per 448-thread block); more: 8-row
+// One pushable block: 9-row columns (13.5 KB per warp, 194 KB per 448-thread block, which still
+// leaves the SM 60 KB of L1 for the manifold records: +1 % over 10-row columns); more: 8-row
 // columns of 56-byte rows (all that fits). A 65536-environment batch puts 7 64-thread blocks (or
 // one 448-thread block) on each SM.
 #ifndef PRL_ROWCAP2
-#define PRL_ROWCAP2 10
+#define PRL_ROWCAP2 9
 #endif
 // (kernels of 64- and 32-thread blocks have no block barrier, so a round only costs the warp that
 // needs it: they keep 7-row columns, which lets seven 64-thread blocks share an SM)

@@ -57,7 +57,7 @@ def many_supports_world(n_posts=6):
     """One pushable plank resting on n fixed posts. Two solver contacts per post plus the
     player's make an environment need more constraint rows than one column of the solver's row
     storage holds, so the warps of the kernels solve in rounds (prl_kernels.cuh,
-    solve_in_rounds): 6 posts = 13 candidate pairs, the small-world kernel (10-row columns, 12-14
+    solve_in_rounds): 6 posts = 13 candidate pairs, the small-world kernel (9-row columns, 12-14
     rows: two rounds); 8 posts = the general kernel (8-row columns, 16-18 rows: four rounds)."""
     objs = []
     for i in range(n_posts):

@@ -134,7 +134,7 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
         static DevWorldSmall S;
         copy_world(S, W);
         if (W.n_bodies == 1) *score = small_pool ? rollout<1, 4>(S, HS_ARGS) : rollout<1, 8>(S, HS_ARGS);
-        else if (W.n_bodies == 2) *score = small_pool ? rollout<2, 4>(S, HS_ARGS) : rollout<2, 10>(S, HS_ARGS);
+        else if (W.n_bodies == 2) *score = small_pool ? rollout<2, 4>(S, HS_ARGS) : rollout<2, 9>(S, HS_ARGS);
         else *score = small_pool ? rollout<MAXB, 4>(S, HS_ARGS) : rollout<MAXB, 8>(S, HS_ARGS);
     } else if (W.n_bodies == 1) {
         *score = small_pool ? rollout<1, 4>(W, HS_ARGS) : rollout<1, 8>(W, HS_ARGS);
