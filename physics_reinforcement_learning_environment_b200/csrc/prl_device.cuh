@@ -7,9 +7,12 @@
 // Design (B200-first, not a translation of rapier's object graph):
 //  * body state lives in registers for the whole launch; a launch runs 1..number_of_steps steps;
 //  * the world's static colliders / pairs / goals are read from a shared-memory DevWorld;
-//  * contact manifolds live in a small per-thread slot table (<= MAXC live manifolds) kept
-//    sorted by pair index through a 64-bit nibble list, so the Gauss-Seidel order is the
-//    canonical ascending (collider1, collider2) order without moving manifold data;
+//  * contact manifolds live in a small per-thread slot table (<= MAXC live manifolds): slot ==
+//    pair index and bit masks for worlds with <= MAXC candidate pairs (every shipped level), else
+//    arbitrary slots kept sorted by pair index through a 64-bit nibble list; either way the
+//    Gauss-Seidel order is the canonical ascending (collider1, collider2) order and no manifold
+//    data ever moves;
+//  * the solver's constraint rows live in shared memory, one column per lane (conflict-free);
 //  * every stage is a flat loop over "my k-th item" so that the lanes of a warp run the narrow
 //    phase / constraint solve of different environments in lockstep instead of serialising;
 //  * arithmetic is f32 in the reference's expression order; the translation unit is compiled
@@ -1494,8 +1497,8 @@ struct Stepper {
     }
 
     // Environment::step (common.rs:215-340) in three parts, so that the collision detection has
-    // one call site and the warp can hand out the solver's row pool between the halves (every
-    // lane of the warp takes part in that hand-out, including lanes whose rollout has ended):
+    // one call site and the warp can agree on the shape of its row storage between the halves (every
+    // lane of the warp takes part in that vote, including lanes whose rollout has ended):
     //
     //   detect_pending();                 // broad + narrow phase owed by the previous position update
     //   need = begin_step(move);          // ground scan + move impulses + constraint selection
