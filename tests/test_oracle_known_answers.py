@@ -123,3 +123,40 @@ def test_early_exit_tail_quirk():
     env = OracleEnv(world_dict("right"))
     score, win, run = env.rollout(np.full(50, 2, np.uint8), 20, 1007)
     assert run == win + 1
+
+
+def test_walking_accelerates_by_impulse_minus_coulomb_friction_and_slides_to_a_stop():
+    """On the flat floor of right.json every grounded step with Move{right} adds 0.003 / m to vx
+    (common.rs:289) and the contact's friction row takes away at most mu * g * dt (mu = 0.5 from
+    rapier's default collider friction, Average rule; g = 2): net +0.003/m - 1/60 per step. With
+    the keys released the player decelerates by exactly mu * g * dt per step until it stops."""
+    env = OracleEnv(world_dict("right"))
+    vx = []
+    for _ in range(60):
+        env.step(2)
+        vx.append(float(env.state()[0][4]))
+    gain = np.diff(vx[5:])
+    assert np.allclose(gain, 0.003 / PLAYER_MASS - 0.5 * 2.0 * DT, atol=2e-5)
+    vx = []
+    for _ in range(40):
+        env.step(0)
+        vx.append(float(env.state()[0][4]))
+    assert np.allclose(np.diff(vx), -0.5 * 2.0 * DT, atol=1e-6)
+    for _ in range(100):
+        env.step(0)
+    st = env.state()[0]
+    assert abs(st[4]) < 1e-5 and abs(st[5]) < 1e-3   # at rest on the floor
+
+
+def test_resting_penetration_is_the_allowed_linear_error():
+    """rapier only pushes a penetration out down to allowed_linear_error (1 mm; the bias
+    erp / dt * clamp(dist + 0.001, ., 0) vanishes there) and the soft constraint sags a little
+    under gravity: a player at rest on the floor sits 1.0-1.3 mm inside it."""
+    world = world_dict("right")
+    env = OracleEnv(world)
+    for _ in range(300):
+        env.step(0)
+    floor = [o for o in world["objects"] if o["object"] != "Goal"][0]
+    top = floor["position"][1] * SCALE + abs(floor["scale"][1]) * SCALE / 2
+    bottom = float(env.state()[0][1]) - (0.0625 + 0.125)
+    assert 0.0010 <= top - bottom <= 0.0013
