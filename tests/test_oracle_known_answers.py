@@ -160,3 +160,44 @@ def test_resting_penetration_is_the_allowed_linear_error():
     top = floor["position"][1] * SCALE + abs(floor["scale"][1]) * SCALE / 2
     bottom = float(env.state()[0][1]) - (0.0625 + 0.125)
     assert 0.0010 <= top - bottom <= 0.0013
+
+
+def test_pushable_block_in_free_fall():
+    """A dynamic cuboid with nothing under it: same semi-implicit Euler as the player, no spin, its
+    rotation (kept as a unit complex, re-normalised every step) unchanged to rounding."""
+    rot = 0.3
+    world = empty_world()
+    world["objects"].append({"object": {"Block": {"fixed": False}}, "position": [200.0, 50.0, 2.0], "scale": [60.0, 20.0], "rotation": rot})
+    env = OracleEnv(world)
+    y0 = 50.0 * SCALE
+    for k in range(1, 121):
+        env.step(0)
+    blk = env.state()[1]
+    k = 120
+    assert abs(blk[0] - 200.0 * SCALE) < 1e-6 and abs(blk[4]) == 0.0 and blk[6] == 0.0
+    assert abs(blk[5] - (-2.0 * DT * k)) < 1e-4
+    assert abs(blk[1] - (y0 - 2.0 * DT * DT * k * (k + 1) / 2)) < 1e-4
+    assert abs(blk[2] - math.cos(rot)) < 1e-5 and abs(blk[3] - math.sin(rot)) < 1e-5
+
+
+def test_momentum_of_player_and_free_block_changes_only_by_gravity():
+    """The player stands on a pushable block and both fall freely (no fixed collider anywhere).
+    Contact impulses act equal and opposite on the two bodies, and so do the move impulses
+    (common.rs:268, 292, 305-306: the reaction -J is applied to the block at the contact point):
+    whatever the moves -- including the jump that separates the two -- the total linear momentum
+    changes by exactly (m_player + m_block) * g * dt per step."""
+    world = empty_world()
+    world["objects"].append({"object": {"Block": {"fixed": False}}, "position": [5.0, -40.0, 2.0], "scale": [120.0, 20.0], "rotation": 0.0})
+    m_block = (120.0 * SCALE) * (20.0 * SCALE)
+    env = OracleEnv(world)
+    rng = np.random.default_rng(0)
+    prev, jumped = None, False
+    for t in range(80):
+        env.step(int(rng.integers(0, 8)) if t > 5 else 0)
+        st = env.state()
+        p = np.array([PLAYER_MASS * st[0][4] + m_block * st[1][4], PLAYER_MASS * st[0][5] + m_block * st[1][5]], np.float64)
+        if prev is not None:
+            assert abs(p[0] - prev[0]) < 1e-7 and abs((p[1] - prev[1]) + (PLAYER_MASS + m_block) * 2.0 * DT) < 1e-7, t
+        jumped = jumped or st[0][5] - st[1][5] > 0.5   # the jump impulse 0.1 / m really separated them
+        prev = p
+    assert jumped
