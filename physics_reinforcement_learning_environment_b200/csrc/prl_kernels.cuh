@@ -6,6 +6,9 @@
 //                    (per-environment moves, or one move for all)
 //   rollout_kernel   the GA fitness rollout (src/main.rs:44-70) for every agent, from a fresh
 //                    from_world state, whole horizon in one launch
+//   trajectory_kernel  the viewer's replay of an agent (src/train.rs:132-159): fresh environments,
+//                    every body recorded after every step
+//   observe_kernel / gather_state_kernel   distance_to_goals / won / body state of the stored batch
 //
 // HBM layout: structure of arrays, word(f, env) = state[f * n + env] (prl_world.h), so a warp's
 // loads and stores of one field are one coalesced 128-byte transaction.
