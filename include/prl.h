@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PRL_ABI_VERSION 1
+#define PRL_ABI_VERSION 2
 
 typedef enum {
     PRL_OK = 0,
@@ -158,29 +158,54 @@ typedef struct {
     uint64_t seed;             /* the reference uses thread_rng (main.rs:42); here a Philox key */
 } prl_ga_config;
 
-/* Population slice [rank*N/n_ranks, (rank+1)*N/n_ranks) lives on `device`. */
+/* Three ways to run the GA (csrc/prl_ga.cu):
+ *  - prl_ga_create(rank 0 of 1): the whole population on one device;
+ *  - prl_ga_create(rank r of R), one process per GPU: this handle owns the slice
+ *    [r*N/R, (r+1)*N/R); the HOST exchanges the generation between prl_ga_best calls
+ *    (ncclAllGather of the local scores and genomes into the global buffers, prl_ga_buffers);
+ *  - prl_ga_create_multi(devices[]): one process, one slice and one stream per device; the
+ *    library exchanges the generation itself over peer memory (NVLink): scores are pushed into
+ *    every peer's score vector, parent genomes are read from the owning device by the breeding
+ *    kernel. Needs peer access between all listed devices. A device may be listed more than once
+ *    (several slices on one GPU).
+ * The result -- every genome and score of every generation -- is the same for all three. */
 int prl_ga_create(const prl_world*, const prl_ga_config*, int32_t device, void* stream,
                   int32_t rank, int32_t n_ranks, prl_ga** out);
+int prl_ga_create_multi(const prl_world*, const prl_ga_config*, const int32_t* devices, int32_t n_devices,
+                        prl_ga** out);
 void prl_ga_destroy(prl_ga*);
-/* main.rs:72-84: random genomes for the local slice and their scores */
+/* slices held by this handle: n_devices for prl_ga_create_multi, else 1 */
+int32_t prl_ga_num_shards(const prl_ga*);
+/* main.rs:72-84: random genomes for the handle's slice(s) and their scores */
 int prl_ga_init(prl_ga*);
-/* Device buffers for the per-generation exchange (ncclAllGather by the host when n_ranks > 1):
- * local_*: this rank's slice; global_*: all agents. With n_ranks == 1 local aliases global. */
+/* Device buffers of a prl_ga_create handle, for the per-generation exchange by the host when
+ * n_ranks > 1: local_*: this rank's slice; global_*: all agents. With n_ranks == 1 local_* and
+ * global_* are the same memory, and the genome pointer is only valid until the next
+ * prl_ga_next_generation (parents and children are two buffers that swap). Not for
+ * prl_ga_create_multi handles (PRL_ERR_INVALID): use prl_ga_read_generation. */
 int prl_ga_buffers(prl_ga*, float** local_scores, uint8_t** local_genomes, float** global_scores,
                    uint8_t** global_genomes, int64_t* local_count, int64_t* local_offset,
                    int32_t* genome_len);
 /* main.rs:87-124: (best score, best genome) of the current global generation; first minimum
  * wins ties. best_genome: genome_len bytes, host or device; outputs may be NULL. With
- * n_ranks == 1 the local slice is first copied into the global buffers (a one-rank all-gather);
- * with n_ranks > 1 the host must have all-gathered them (prl_ga_buffers). */
+ * n_ranks > 1 the host must have all-gathered the generation (prl_ga_buffers). Synchronises.
+ * Returns PRL_ERR_OVERFLOW if an agent's environment ran out of contact-manifold slots while it
+ * was scored (its score is not exact). */
 int prl_ga_best(prl_ga*, float* best_score, uint8_t* best_genome, int64_t* best_index);
-/* main.rs:126-160 for the local slice: elitism, weighted 2-parent choice, crossover, mutation,
- * then scores the children. Reads the global buffers (which the host has all-gathered). */
+/* main.rs:126-160 for the handle's slice(s): elitism, weighted 2-parent choice, crossover,
+ * mutation, then scores the children. */
 int prl_ga_next_generation(prl_ga*);
+/* One iteration of the loop at main.rs:86-162 for single-process handles (prl_ga_create with
+ * n_ranks == 1, prl_ga_create_multi): reports the best agent of the current generation (the first
+ * call initialises the population, main.rs:72-84), then breeds and scores the next one. */
+int prl_ga_step_generation(prl_ga*, float* best_score, uint8_t* best_genome, int64_t* best_index);
+/* the whole current generation to the host (single-process handles): scores: number_of_agents
+ * floats, genomes: number_of_agents x genome_len Moves; either may be NULL */
+int prl_ga_read_generation(prl_ga*, float* scores, uint8_t* genomes);
 int64_t prl_ga_generation(const prl_ga*);
 int64_t prl_ga_launch_count(const prl_ga*);
-/* environment steps executed by the local slice's most recent scoring pass (early exit on win
- * makes this less than n_local * number_of_steps); -1 on CUDA failure */
+/* environment steps executed by the most recent scoring pass of the handle's slice(s) (early exit
+ * on win makes this less than n_local * number_of_steps); -1 on CUDA failure */
 int64_t prl_ga_env_steps(prl_ga*);
 
 #ifdef __cplusplus

@@ -73,13 +73,17 @@ _SIGNATURES = {
     "prl_batch_launch_count": (C.c_int64, [C.c_void_p]),
     "prl_ga_create": (C.c_int, [C.c_void_p, C.POINTER(PrlGaConfig), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,
                                 C.POINTER(C.c_void_p)]),
+    "prl_ga_create_multi": (C.c_int, [C.c_void_p, C.POINTER(PrlGaConfig), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_void_p)]),
     "prl_ga_destroy": (None, [C.c_void_p]),
+    "prl_ga_num_shards": (C.c_int32, [C.c_void_p]),
     "prl_ga_init": (C.c_int, [C.c_void_p]),
     "prl_ga_buffers": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                  C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                  C.POINTER(C.c_int32)]),
     "prl_ga_best": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int64)]),
     "prl_ga_next_generation": (C.c_int, [C.c_void_p]),
+    "prl_ga_step_generation": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.c_void_p, C.POINTER(C.c_int64)]),
+    "prl_ga_read_generation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_ga_generation": (C.c_int64, [C.c_void_p]),
     "prl_ga_launch_count": (C.c_int64, [C.c_void_p]),
     "prl_ga_env_steps": (C.c_int64, [C.c_void_p]),

@@ -154,20 +154,19 @@ int prl_batch_create(const prl_world* w, int64_t n_envs, int32_t device, void* s
     b->stream = (cudaStream_t)stream;
     if (cudaDeviceGetAttribute(&b->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) b->sm_count = 148;
     b->words = state_words(w->dev.n_bodies, w->dev.n_slots);
-    cudaError_t e1 = cudaMalloc(&b->dev_world, sizeof(DevWorld));
-    cudaError_t e2 = e1 == cudaSuccess ? cudaMalloc(&b->state, (size_t)b->words * (size_t)n_envs * 4u) : e1;
+    cudaError_t e2 = cudaMalloc(&b->dev_world, sizeof(DevWorld));
+    if (e2 == cudaSuccess) e2 = cudaMalloc(&b->state, (size_t)b->words * (size_t)n_envs * 4u);
     if (e2 == cudaSuccess) e2 = cudaMalloc(&b->overflow, sizeof(int));
     if (e2 != cudaSuccess) {
         set_error("cudaMalloc of %d state words x %lld environments failed: %s", b->words, (long long)n_envs, cudaGetErrorString(e2));
-        if (b->dev_world) cudaFree(b->dev_world);
-        delete b;
+        prl_batch_destroy(b);
         return PRL_ERR_CUDA;
     }
     cudaError_t e3 = cudaMemcpyAsync(b->dev_world, &b->host_world, sizeof(DevWorld), cudaMemcpyHostToDevice, b->stream);
     if (e3 == cudaSuccess) e3 = cudaStreamSynchronize(b->stream);
     if (e3 != cudaSuccess) {
         set_error("uploading the world tables failed: %s", cudaGetErrorString(e3));
-        cudaFree(b->dev_world); cudaFree(b->state); delete b;
+        prl_batch_destroy(b);
         return PRL_ERR_CUDA;
     }
     int rc = prl_batch_reset(b);

@@ -16,37 +16,74 @@
 // so a child's genome does not depend on how the population is sharded over GPUs. (The reference
 // itself is not reproducible: thread_rng, main.rs:42.)
 //
-// Multi-GPU: each rank owns the slice [rank*N/R, (rank+1)*N/R) of the population. After scoring,
-// the host all-gathers the local scores and genomes into the global buffers (NCCL over NVLink,
-// see prl_ga_buffers); every rank then computes the same best / prefix sums and breeds only its
-// own children. The physics itself needs no communication.
+// Multi-GPU. The population is cut into contiguous slices [r*N/R, (r+1)*N/R); the physics needs no
+// communication, selection needs every score (the reference draws parents from the WHOLE
+// generation, main.rs:134-138) and the genomes of the parents actually drawn. Three ways to run:
+//   one shard        prl_ga_create(rank 0 of 1): parents and children are two buffers that swap,
+//                    nothing is copied between generations;
+//   host exchange    prl_ga_create(rank r of R), one process per GPU: the host all-gathers the
+//                    local scores and genomes into the global buffers once per generation
+//                    (ncclAllGather through torch.distributed, genetic.py / parallel.py);
+//   peer shards      prl_ga_create_multi(devices[]): one process, one shard and one stream per
+//                    device. After scoring, every shard pushes its 4 B/agent of scores into its
+//                    peers' copies of the score vector (cudaMemcpyPeerAsync over NVLink, ordered
+//                    by events, no host synchronisation), and the breeding kernel of every shard
+//                    then reads the genomes of the parents it drew STRAIGHT FROM THE OWNING
+//                    SHARD'S MEMORY through peer-mapped pointers: the 100 B/agent genome
+//                    all-gather (100 MB per generation per GPU at one million agents) is never
+//                    made -- each child pulls its two parents, 2 x genome_len bytes, over NVLink.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "prl_batch.h"
 
 using namespace prl;
 
-struct prl_ga {
-    prl_ga_config cfg;
+namespace {
+constexpr int kMaxShards = 16;
+
+// where the breeding kernel finds the genome of parent p: the shard that owns agent p
+struct ParentTable {
+    const uint8_t* base[kMaxShards];  // genomes of agents [off[k], off[k+1])
+    int64_t off[kMaxShards + 1];
+    int n;
+};
+
+// One slice of the population on one device.
+struct GaShard {
     int device = 0;
     cudaStream_t stream = nullptr;
-    int rank = 0, n_ranks = 1;
-    int64_t n_global = 0, local_off = 0, n_local = 0;
-    int genome_len = 0;
+    bool own_stream = false;
+    int64_t local_off = 0, n_local = 0;
     prl_batch* batch = nullptr;
-    uint8_t* local_genomes = nullptr;   // n_local x genome_len
-    float* local_scores = nullptr;      // n_local
-    uint8_t* global_genomes = nullptr;  // n_global x genome_len (parents)
+    uint8_t* genomes[2] = {nullptr, nullptr};  // [cur] = the current (scored) generation of the slice
+    int cur = 0;
+    float* local_scores = nullptr;      // n_local; peer / single shards: global_scores + local_off
+    bool scores_aliased = false;
+    uint8_t* global_genomes = nullptr;  // host-exchange mode only: n_global x genome_len
     float* global_scores = nullptr;     // n_global
     unsigned long long* cdf = nullptr;  // n_global inclusive prefix sums of the fixed-point weights
     unsigned long long* block_sums = nullptr;
     unsigned long long* best_key = nullptr;  // [0] = score bits << 32 | index (min), [1] = max score bits
     unsigned long long* steps_sum = nullptr;
-    int64_t generation = 0;
+    cudaEvent_t scored = nullptr;       // peer mode: my scores have landed in every peer's score vector
     int64_t launches = 0;
+};
+}  // namespace
+
+struct prl_ga {
+    enum Mode { SINGLE, HOST_EXCHANGE, PEER };
+    prl_ga_config cfg;
+    Mode mode = SINGLE;
+    int rank = 0, n_ranks = 1;          // host-exchange mode: my rank among the processes
+    int64_t n_global = 0;
+    int genome_len = 0;
+    std::vector<GaShard> shards;
+    int64_t generation = -1;            // -1: prl_ga_init not called yet
     bool best_valid = false;
     float best_score = 0.0f, max_score = 0.0f;
     int64_t best_index = 0;
@@ -190,7 +227,12 @@ __device__ __forceinline__ int64_t pick(const unsigned long long* __restrict__ c
 }
 
 // main.rs:126-158 for the children [local_off, local_off + n_local)
-__global__ void breed_kernel(const uint8_t* __restrict__ parents, const unsigned long long* __restrict__ cdf, int64_t n_global, int genome_len,
+__device__ __forceinline__ const uint8_t* parent_genome(const ParentTable& pt, int64_t p, int genome_len) {
+    int k = 0;
+    while (k + 1 < pt.n && p >= pt.off[k + 1]) ++k;
+    return pt.base[k] + (p - pt.off[k]) * genome_len;
+}
+__global__ void breed_kernel(const ParentTable pt, const unsigned long long* __restrict__ cdf, int64_t n_global, int genome_len,
                              uint8_t* __restrict__ children, int64_t n_local, int64_t local_off, float mutation_rate, int keep_best,
                              int64_t best_index, uint64_t seed, uint32_t generation) {
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -198,7 +240,7 @@ __global__ void breed_kernel(const uint8_t* __restrict__ parents, const unsigned
     int64_t child = local_off + t;
     uint8_t* out = children + t * genome_len;
     if (keep_best && child == 0) {  // new_generation = vec![min_agent.clone()]
-        const uint8_t* src = parents + best_index * genome_len;
+        const uint8_t* src = parent_genome(pt, best_index, genome_len);
         for (int g = 0; g < genome_len; ++g) out[g] = src[g];
         return;
     }
@@ -213,8 +255,9 @@ __global__ void breed_kernel(const uint8_t* __restrict__ parents, const unsigned
         if (p2 == p1) p2 = pick(cdf, n_global, total, r[2], r[3]);
     }
     if (p2 == p1 && n_global > 1) p2 = (p1 + 1) % n_global;
-    const uint8_t* g1 = parents + p1 * genome_len;
-    const uint8_t* g2 = parents + p2 * genome_len;
+    // the parents may live on another GPU (peer shards): 2 x genome_len bytes over NVLink
+    const uint8_t* g1 = parent_genome(pt, p1, genome_len);
+    const uint8_t* g2 = parent_genome(pt, p2, genome_len);
     for (int g = 0; g < genome_len; ++g) {
         philox4x32(seed, (uint64_t)child, generation, (uint32_t)g, r);
         uint32_t mv = (r[0] >> 31) ? g1[g] : g2[g];  // rng.gen::<bool>()
@@ -238,11 +281,133 @@ __global__ void sum_steps_kernel(const uint32_t* __restrict__ steps, int64_t n, 
 
 inline unsigned blocks_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
-int score_local(prl_ga* ga) {
-    int rc = prl_batch_rollout(ga->batch, ga->local_genomes, ga->genome_len, ga->cfg.repeat_move, ga->cfg.number_of_steps, 1,
-                               ga->local_scores, nullptr);
+int validate_config(const prl_world* w, const prl_ga_config* cfg) {
+    if (cfg->number_of_agents < 2 || cfg->repeat_move < 1 || cfg->number_of_steps < 1 || cfg->number_of_steps / cfg->repeat_move < 1) {
+        set_error("prl_ga_create: need number_of_agents >= 2 (two distinct parents, main.rs:134-138), repeat_move >= 1 and number_of_steps >= repeat_move");
+        return PRL_ERR_INVALID;
+    }
+    if (cfg->number_of_agents > 0xffffffffll) { set_error("prl_ga_create: number_of_agents exceeds 2^32-1"); return PRL_ERR_INVALID; }
+    if (w->dev.n_goals == 0) { set_error("the world has no goal: agent_score's distance_to_goals().unwrap() would panic (main.rs:50)"); return PRL_ERR_NO_GOAL; }
+    return PRL_OK;
+}
+
+// device memory of one shard; `stream` == nullptr and own_stream: the shard makes its own
+int shard_alloc(prl_ga* ga, GaShard& s, const prl_world* w) {
+    DeviceGuard g(s.device);
+    if (s.own_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    int rc = prl_batch_create(w, s.n_local, s.device, s.stream, &s.batch);
+    if (rc != PRL_OK) return rc;
+    const size_t L = (size_t)ga->genome_len;
+    const int64_t nblocks = (ga->n_global + kScanChunk - 1) / kScanChunk;
+    cudaError_t e = cudaMalloc(&s.genomes[0], (size_t)s.n_local * L);
+    // host-exchange shards breed from the gathered copy into their slice in place (the host keeps
+    // pointers to both); the others alternate between two buffers
+    if (e == cudaSuccess && ga->mode != prl_ga::HOST_EXCHANGE) e = cudaMalloc(&s.genomes[1], (size_t)s.n_local * L);
+    if (e == cudaSuccess) e = cudaMalloc(&s.global_scores, (size_t)ga->n_global * 4);
+    if (e == cudaSuccess && ga->mode == prl_ga::HOST_EXCHANGE) {
+        e = cudaMalloc(&s.global_genomes, (size_t)ga->n_global * L);
+        if (e == cudaSuccess) e = cudaMalloc(&s.local_scores, (size_t)s.n_local * 4);
+    } else if (e == cudaSuccess) {
+        s.local_scores = s.global_scores + s.local_off;  // my rollouts write their scores in place
+        s.scores_aliased = true;
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&s.cdf, (size_t)ga->n_global * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s.block_sums, (size_t)nblocks * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&s.best_key, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&s.steps_sum, 8);
+    if (e == cudaSuccess && ga->mode == prl_ga::PEER) e = cudaEventCreateWithFlags(&s.scored, cudaEventDisableTiming);
+    if (e != cudaSuccess) { set_error("prl_ga_create: device allocation failed on device %d: %s", s.device, cudaGetErrorString(e)); return PRL_ERR_CUDA; }
+    return PRL_OK;
+}
+
+void shard_free(GaShard& s) {
+    {
+        DeviceGuard g(s.device);
+        if (s.stream || !s.own_stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.genomes[0]); cudaFree(s.genomes[1]); cudaFree(s.global_genomes); cudaFree(s.global_scores);
+        if (!s.scores_aliased) cudaFree(s.local_scores);
+        cudaFree(s.cdf); cudaFree(s.block_sums); cudaFree(s.best_key); cudaFree(s.steps_sum);
+        if (s.scored) cudaEventDestroy(s.scored);
+    }
+    prl_batch_destroy(s.batch);
+    if (s.own_stream && s.stream) { DeviceGuard g(s.device); cudaStreamDestroy(s.stream); }
+}
+
+// main.rs:44-70 for every agent of the shard (asynchronous on the shard's stream)
+int shard_score(prl_ga* ga, GaShard& s) {
+    return prl_batch_rollout(s.batch, s.genomes[s.cur], ga->genome_len, ga->cfg.repeat_move, ga->cfg.number_of_steps, 1, s.local_scores, nullptr);
+}
+
+// peer shards: every shard's fresh scores into every other shard's score vector, ordered by
+// events: a shard's stream continues only when all slices have arrived in its copy. No host sync.
+int exchange_scores(prl_ga* ga) {
+    if (ga->mode != prl_ga::PEER) return PRL_OK;
+    for (GaShard& s : ga->shards) {
+        DeviceGuard g(s.device);
+        for (GaShard& d : ga->shards) {
+            if (&d == &s) continue;
+            CUDA_TRY(cudaMemcpyPeerAsync(d.global_scores + s.local_off, d.device, s.local_scores, s.device, (size_t)s.n_local * 4, s.stream));
+        }
+        CUDA_TRY(cudaEventRecord(s.scored, s.stream));
+    }
+    for (GaShard& d : ga->shards) {
+        DeviceGuard g(d.device);
+        for (GaShard& s : ga->shards)
+            if (&d != &s) CUDA_TRY(cudaStreamWaitEvent(d.stream, s.scored, 0));
+    }
+    return PRL_OK;
+}
+
+int score_all(prl_ga* ga) {
     ga->best_valid = false;
-    return rc;
+    for (GaShard& s : ga->shards) {
+        int rc = shard_score(ga, s);
+        if (rc != PRL_OK) return rc;
+    }
+    return exchange_scores(ga);
+}
+
+ParentTable parent_table(const prl_ga* ga, const GaShard& me) {
+    ParentTable pt;
+    memset(&pt, 0, sizeof(pt));
+    if (ga->mode == prl_ga::HOST_EXCHANGE) {
+        pt.n = 1; pt.base[0] = me.global_genomes; pt.off[0] = 0; pt.off[1] = ga->n_global;
+        return pt;
+    }
+    pt.n = (int)ga->shards.size();
+    for (int k = 0; k < pt.n; ++k) { pt.base[k] = ga->shards[k].genomes[ga->shards[k].cur]; pt.off[k] = ga->shards[k].local_off; }
+    pt.off[pt.n] = ga->n_global;
+    return pt;
+}
+
+int create_common(const prl_world* w, const prl_ga_config* cfg, prl_ga::Mode mode, int rank, int n_ranks, const int32_t* devices, int n_shards,
+                  void* stream, prl_ga** out) {
+    prl_ga* ga = new (std::nothrow) prl_ga();
+    if (!ga) { set_error("out of memory"); return PRL_ERR_INVALID; }
+    ga->cfg = *cfg;
+    ga->mode = mode;
+    ga->rank = rank;
+    ga->n_ranks = n_ranks;
+    ga->n_global = cfg->number_of_agents;
+    ga->genome_len = cfg->number_of_steps / cfg->repeat_move;  // main.rs:75
+    ga->shards.resize(n_shards);
+    const int parts = mode == prl_ga::HOST_EXCHANGE ? n_ranks : n_shards;
+    for (int k = 0; k < n_shards; ++k) {
+        GaShard& s = ga->shards[k];
+        const int r = mode == prl_ga::HOST_EXCHANGE ? rank : k;
+        s.device = devices[k];
+        s.stream = mode == prl_ga::PEER ? nullptr : (cudaStream_t)stream;
+        s.own_stream = mode == prl_ga::PEER;
+        s.local_off = ga->n_global * r / parts;
+        s.n_local = ga->n_global * (r + 1) / parts - s.local_off;
+        if (s.n_local < 1) { set_error("prl_ga_create: slice %d of %d owns no agent", r, parts); prl_ga_destroy(ga); return PRL_ERR_INVALID; }
+    }
+    for (GaShard& s : ga->shards) {
+        int rc = shard_alloc(ga, s, w);
+        if (rc != PRL_OK) { prl_ga_destroy(ga); return rc; }
+    }
+    *out = ga;
+    return PRL_OK;
 }
 
 }  // namespace
@@ -251,113 +416,128 @@ extern "C" {
 
 int prl_ga_create(const prl_world* w, const prl_ga_config* cfg, int32_t device, void* stream, int32_t rank, int32_t n_ranks, prl_ga** out) {
     if (!w || !cfg || !out || n_ranks < 1 || rank < 0 || rank >= n_ranks) { set_error("prl_ga_create: bad argument"); return PRL_ERR_INVALID; }
-    if (cfg->number_of_agents < 2 || cfg->repeat_move < 1 || cfg->number_of_steps < 1 || cfg->number_of_steps / cfg->repeat_move < 1) {
-        set_error("prl_ga_create: need number_of_agents >= 2 (two distinct parents, main.rs:134-138), repeat_move >= 1 and number_of_steps >= repeat_move");
+    int rc = validate_config(w, cfg);
+    if (rc != PRL_OK) return rc;
+    return create_common(w, cfg, n_ranks == 1 ? prl_ga::SINGLE : prl_ga::HOST_EXCHANGE, rank, n_ranks, &device, 1, stream, out);
+}
+
+int prl_ga_create_multi(const prl_world* w, const prl_ga_config* cfg, const int32_t* devices, int32_t n_devices, prl_ga** out) {
+    if (!w || !cfg || !out || !devices || n_devices < 1 || n_devices > kMaxShards) {
+        set_error("prl_ga_create_multi: bad argument (1..%d devices)", kMaxShards);
         return PRL_ERR_INVALID;
     }
-    if (cfg->number_of_agents > 0xffffffffll) { set_error("prl_ga_create: number_of_agents exceeds 2^32-1"); return PRL_ERR_INVALID; }
-    if (w->dev.n_goals == 0) { set_error("the world has no goal: agent_score's distance_to_goals().unwrap() would panic (main.rs:50)"); return PRL_ERR_NO_GOAL; }
-    prl_ga* ga = new (std::nothrow) prl_ga();
-    if (!ga) { set_error("out of memory"); return PRL_ERR_INVALID; }
-    ga->cfg = *cfg;
-    ga->device = device;
-    ga->stream = (cudaStream_t)stream;
-    ga->rank = rank;
-    ga->n_ranks = n_ranks;
-    ga->n_global = cfg->number_of_agents;
-    ga->local_off = ga->n_global * rank / n_ranks;
-    ga->n_local = ga->n_global * (rank + 1) / n_ranks - ga->local_off;
-    ga->genome_len = cfg->number_of_steps / cfg->repeat_move;  // main.rs:75
-    if (ga->n_local < 1) { set_error("prl_ga_create: rank %d of %d owns no agent", rank, n_ranks); delete ga; return PRL_ERR_INVALID; }
-    int rc = prl_batch_create(w, ga->n_local, device, stream, &ga->batch);
-    if (rc != PRL_OK) { delete ga; return rc; }
-    DeviceGuard g(device);
-    size_t L = (size_t)ga->genome_len;
-    int64_t nblocks = (ga->n_global + kScanChunk - 1) / kScanChunk;
-    cudaError_t e = cudaMalloc(&ga->local_genomes, (size_t)ga->n_local * L);
-    if (e == cudaSuccess) e = cudaMalloc(&ga->local_scores, (size_t)ga->n_local * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&ga->global_genomes, (size_t)ga->n_global * L);
-    if (e == cudaSuccess) e = cudaMalloc(&ga->global_scores, (size_t)ga->n_global * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&ga->cdf, (size_t)ga->n_global * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&ga->block_sums, (size_t)nblocks * 8);
-    if (e == cudaSuccess) e = cudaMalloc(&ga->best_key, 16);
-    if (e == cudaSuccess) e = cudaMalloc(&ga->steps_sum, 8);
-    if (e != cudaSuccess) {
-        set_error("prl_ga_create: cudaMalloc failed: %s", cudaGetErrorString(e));
-        prl_ga_destroy(ga);
+    int rc = validate_config(w, cfg);
+    if (rc != PRL_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device is usable; this library has no CPU path");
         return PRL_ERR_CUDA;
     }
-    *out = ga;
-    return PRL_OK;
+    for (int a = 0; a < n_devices; ++a)
+        if (devices[a] < 0 || devices[a] >= ndev) { set_error("prl_ga_create_multi: device %d out of range (%d visible)", devices[a], ndev); return PRL_ERR_INVALID; }
+    // every shard reads its peers' genomes and writes their score vectors directly
+    for (int a = 0; a < n_devices; ++a) {
+        DeviceGuard g(devices[a]);
+        for (int b = 0; b < n_devices; ++b) {
+            if (devices[a] == devices[b]) continue;
+            int can = 0;
+            CUDA_TRY(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
+            if (!can) { set_error("prl_ga_create_multi: device %d cannot map the memory of device %d (no NVLink / PCIe peer path)", devices[a], devices[b]); return PRL_ERR_CUDA; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else CUDA_TRY(e);
+        }
+    }
+    return create_common(w, cfg, prl_ga::PEER, 0, 1, devices, n_devices, nullptr, out);
 }
 
 void prl_ga_destroy(prl_ga* ga) {
     if (!ga) return;
-    {
-        DeviceGuard g(ga->device);
-        cudaStreamSynchronize(ga->stream);
-        cudaFree(ga->local_genomes); cudaFree(ga->local_scores); cudaFree(ga->global_genomes); cudaFree(ga->global_scores);
-        cudaFree(ga->cdf); cudaFree(ga->block_sums); cudaFree(ga->best_key); cudaFree(ga->steps_sum);
-    }
-    prl_batch_destroy(ga->batch);
+    // nobody may still be reading a peer's memory when it is freed
+    for (GaShard& s : ga->shards) { DeviceGuard g(s.device); if (s.stream || !s.own_stream) cudaStreamSynchronize(s.stream); }
+    for (GaShard& s : ga->shards) shard_free(s);
     delete ga;
 }
 
+int32_t prl_ga_num_shards(const prl_ga* ga) { return ga ? (int32_t)ga->shards.size() : 0; }
+
 int prl_ga_init(prl_ga* ga) {
     if (!ga) { set_error("prl_ga_init: null handle"); return PRL_ERR_INVALID; }
-    DeviceGuard g(ga->device);
-    int64_t total = ga->n_local * ga->genome_len;
-    init_genomes_kernel<<<blocks_for(total, kGaBlock), kGaBlock, 0, ga->stream>>>(ga->local_genomes, ga->n_local, ga->local_off, ga->genome_len, ga->cfg.seed);
-    ++ga->launches;
-    CUDA_TRY(cudaGetLastError());
+    for (GaShard& s : ga->shards) {
+        DeviceGuard g(s.device);
+        s.cur = 0;
+        int64_t total = s.n_local * ga->genome_len;
+        init_genomes_kernel<<<blocks_for(total, kGaBlock), kGaBlock, 0, s.stream>>>(s.genomes[0], s.n_local, s.local_off, ga->genome_len, ga->cfg.seed);
+        ++s.launches;
+        CUDA_TRY(cudaGetLastError());
+    }
     ga->generation = 0;
-    return score_local(ga);
+    return score_all(ga);
 }
 
 int prl_ga_buffers(prl_ga* ga, float** local_scores, uint8_t** local_genomes, float** global_scores, uint8_t** global_genomes,
                    int64_t* local_count, int64_t* local_offset, int32_t* genome_len) {
     if (!ga) { set_error("prl_ga_buffers: null handle"); return PRL_ERR_INVALID; }
-    if (local_scores) *local_scores = ga->local_scores;
-    if (local_genomes) *local_genomes = ga->local_genomes;
-    if (global_scores) *global_scores = ga->global_scores;
-    if (global_genomes) *global_genomes = ga->global_genomes;
-    if (local_count) *local_count = ga->n_local;
-    if (local_offset) *local_offset = ga->local_off;
+    if (ga->mode == prl_ga::PEER) { set_error("prl_ga_buffers: a prl_ga_create_multi handle exchanges its generation itself; read it with prl_ga_read_generation"); return PRL_ERR_INVALID; }
+    GaShard& s = ga->shards[0];
+    if (local_scores) *local_scores = s.local_scores;
+    if (local_genomes) *local_genomes = s.genomes[s.cur];
+    if (global_scores) *global_scores = s.global_scores;
+    if (global_genomes) *global_genomes = ga->mode == prl_ga::SINGLE ? s.genomes[s.cur] : s.global_genomes;
+    if (local_count) *local_count = s.n_local;
+    if (local_offset) *local_offset = s.local_off;
     if (genome_len) *genome_len = ga->genome_len;
     return PRL_OK;
 }
 
 int prl_ga_best(prl_ga* ga, float* best_score, uint8_t* best_genome, int64_t* best_index) {
     if (!ga) { set_error("prl_ga_best: null handle"); return PRL_ERR_INVALID; }
-    DeviceGuard g(ga->device);
+    if (ga->generation < 0) { set_error("prl_ga_best: call prl_ga_init first"); return PRL_ERR_INVALID; }
     if (!ga->best_valid) {
-        if (ga->n_ranks == 1) {
-            // a single rank is its own all-gather
-            CUDA_TRY(cudaMemcpyAsync(ga->global_scores, ga->local_scores, (size_t)ga->n_local * 4, cudaMemcpyDeviceToDevice, ga->stream));
-            CUDA_TRY(cudaMemcpyAsync(ga->global_genomes, ga->local_genomes, (size_t)ga->n_local * ga->genome_len, cudaMemcpyDeviceToDevice, ga->stream));
+        // every shard reduces its own copy of the score vector (they are identical); all shards are
+        // queued before the first is waited for
+        unsigned long long keys[kMaxShards][2];
+        int over[kMaxShards];
+        const unsigned long long init[2] = {~0ull, 0ull};
+        for (size_t k = 0; k < ga->shards.size(); ++k) {
+            GaShard& s = ga->shards[k];
+            DeviceGuard g(s.device);
+            CUDA_TRY(cudaMemcpyAsync(s.best_key, init, 16, cudaMemcpyHostToDevice, s.stream));
+            unsigned nb = blocks_for(ga->n_global, kGaBlock);
+            if (nb > 1184) nb = 1184;  // 148 SMs x 8 resident blocks, grid-stride
+            best_kernel<<<nb, kGaBlock, 0, s.stream>>>(s.global_scores, ga->n_global, s.best_key);
+            ++s.launches;
+            CUDA_TRY(cudaGetLastError());
+            CUDA_TRY(cudaMemcpyAsync(keys[k], s.best_key, 16, cudaMemcpyDeviceToHost, s.stream));
+            CUDA_TRY(cudaMemcpyAsync(&over[k], s.batch->overflow, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
         }
-        unsigned long long init[2] = {~0ull, 0ull};
-        CUDA_TRY(cudaMemcpyAsync(ga->best_key, init, 16, cudaMemcpyHostToDevice, ga->stream));
-        unsigned nb = blocks_for(ga->n_global, kGaBlock);
-        if (nb > 1184) nb = 1184;  // 148 SMs x 8 resident blocks, grid-stride
-        best_kernel<<<nb, kGaBlock, 0, ga->stream>>>(ga->global_scores, ga->n_global, ga->best_key);
-        ++ga->launches;
-        CUDA_TRY(cudaGetLastError());
-        unsigned long long keys[2];
-        CUDA_TRY(cudaMemcpyAsync(keys, ga->best_key, 16, cudaMemcpyDeviceToHost, ga->stream));
-        CUDA_TRY(cudaStreamSynchronize(ga->stream));
-        uint32_t bmin = (uint32_t)(keys[0] >> 32), bmax = (uint32_t)keys[1];
+        for (GaShard& s : ga->shards) { DeviceGuard g(s.device); CUDA_TRY(cudaStreamSynchronize(s.stream)); }
+        for (size_t k = 0; k < ga->shards.size(); ++k) {
+            if (over[k]) {
+                set_error("an agent's environment needed more than PRL_MAX_CONTACTS=%d simultaneous contact manifolds: its score is not exact, the generation is not usable", PRL_MAX_CONTACTS);
+                return PRL_ERR_OVERFLOW;
+            }
+            if (keys[k][0] != keys[0][0] || keys[k][1] != keys[0][1]) { set_error("prl_ga_best: the shards disagree on the generation (internal error)"); return PRL_ERR_CUDA; }
+        }
+        uint32_t bmin = (uint32_t)(keys[0][0] >> 32), bmax = (uint32_t)keys[0][1];
         memcpy(&ga->best_score, &bmin, 4);
         memcpy(&ga->max_score, &bmax, 4);
-        ga->best_index = (int64_t)(keys[0] & 0xffffffffull);
+        ga->best_index = (int64_t)(keys[0][0] & 0xffffffffull);
         ga->best_valid = true;
     }
     if (best_score) *best_score = ga->best_score;
     if (best_index) *best_index = ga->best_index;
     if (best_genome) {
-        CUDA_TRY(cudaMemcpyAsync(best_genome, ga->global_genomes + (size_t)ga->best_index * ga->genome_len, (size_t)ga->genome_len,
-                                 cudaMemcpyDefault, ga->stream));
-        CUDA_TRY(cudaStreamSynchronize(ga->stream));
+        GaShard& s0 = ga->shards[0];
+        const ParentTable pt = parent_table(ga, s0);
+        int k = 0;
+        while (k + 1 < pt.n && ga->best_index >= pt.off[k + 1]) ++k;
+        GaShard& owner = ga->mode == prl_ga::PEER ? ga->shards[k] : s0;
+        DeviceGuard g(owner.device);
+        CUDA_TRY(cudaMemcpyAsync(best_genome, pt.base[k] + (size_t)(ga->best_index - pt.off[k]) * ga->genome_len, (size_t)ga->genome_len,
+                                 cudaMemcpyDefault, owner.stream));
+        CUDA_TRY(cudaStreamSynchronize(owner.stream));
     }
     return PRL_OK;
 }
@@ -366,35 +546,90 @@ int prl_ga_next_generation(prl_ga* ga) {
     if (!ga) { set_error("prl_ga_next_generation: null handle"); return PRL_ERR_INVALID; }
     int rc = prl_ga_best(ga, nullptr, nullptr, nullptr);
     if (rc != PRL_OK) return rc;
-    DeviceGuard g(ga->device);
-    int64_t nblocks = (ga->n_global + kScanChunk - 1) / kScanChunk;
-    weight_block_sums_kernel<<<(unsigned)nblocks, kGaBlock, 0, ga->stream>>>(ga->global_scores, ga->n_global, ga->max_score, ga->block_sums);
-    scan_block_sums_kernel<<<1, 32, 0, ga->stream>>>(ga->block_sums, nblocks);
-    weight_scan_kernel<<<(unsigned)nblocks, kGaBlock, 0, ga->stream>>>(ga->global_scores, ga->n_global, ga->max_score, ga->block_sums, ga->cdf);
+    const int64_t nblocks = (ga->n_global + kScanChunk - 1) / kScanChunk;
     ++ga->generation;
-    breed_kernel<<<blocks_for(ga->n_local, kGaBlock), kGaBlock, 0, ga->stream>>>(
-        ga->global_genomes, ga->cdf, ga->n_global, ga->genome_len, ga->local_genomes, ga->n_local, ga->local_off, ga->cfg.mutation_rate,
-        ga->cfg.keep_best, ga->best_index, ga->cfg.seed, (uint32_t)ga->generation);
-    ga->launches += 4;
-    CUDA_TRY(cudaGetLastError());
-    return score_local(ga);
+    // breeding reads the current buffers of every shard, so all tables are taken before any swap
+    ParentTable tables[kMaxShards];
+    for (size_t k = 0; k < ga->shards.size(); ++k) tables[k] = parent_table(ga, ga->shards[k]);
+    for (size_t k = 0; k < ga->shards.size(); ++k) {
+        GaShard& s = ga->shards[k];
+        DeviceGuard g(s.device);
+        weight_block_sums_kernel<<<(unsigned)nblocks, kGaBlock, 0, s.stream>>>(s.global_scores, ga->n_global, ga->max_score, s.block_sums);
+        scan_block_sums_kernel<<<1, 32, 0, s.stream>>>(s.block_sums, nblocks);
+        weight_scan_kernel<<<(unsigned)nblocks, kGaBlock, 0, s.stream>>>(s.global_scores, ga->n_global, ga->max_score, s.block_sums, s.cdf);
+        uint8_t* children = ga->mode == prl_ga::HOST_EXCHANGE ? s.genomes[0] : s.genomes[s.cur ^ 1];
+        breed_kernel<<<blocks_for(s.n_local, kGaBlock), kGaBlock, 0, s.stream>>>(
+            tables[k], s.cdf, ga->n_global, ga->genome_len, children, s.n_local, s.local_off, ga->cfg.mutation_rate, ga->cfg.keep_best,
+            ga->best_index, ga->cfg.seed, (uint32_t)ga->generation);
+        s.launches += 4;
+        CUDA_TRY(cudaGetLastError());
+        if (ga->mode == prl_ga::PEER) CUDA_TRY(cudaEventRecord(s.scored, s.stream));  // here: "my breeding has read its parents"
+    }
+    if (ga->mode == prl_ga::PEER) {
+        // a shard's rollouts overwrite its slice of every score vector, and two generations on its
+        // next breeding overwrites the buffer its peers are reading parents from now: both wait
+        // until every shard has bred
+        for (GaShard& d : ga->shards) {
+            DeviceGuard g(d.device);
+            for (GaShard& s : ga->shards)
+                if (&d != &s) CUDA_TRY(cudaStreamWaitEvent(d.stream, s.scored, 0));
+        }
+    }
+    if (ga->mode != prl_ga::HOST_EXCHANGE)
+        for (GaShard& s : ga->shards) s.cur ^= 1;
+    return score_all(ga);
 }
 
-int64_t prl_ga_generation(const prl_ga* ga) { return ga ? ga->generation : 0; }
-int64_t prl_ga_launch_count(const prl_ga* ga) { return ga ? ga->launches + prl_batch_launch_count(ga->batch) : 0; }
+int prl_ga_step_generation(prl_ga* ga, float* best_score, uint8_t* best_genome, int64_t* best_index) {
+    if (!ga) { set_error("prl_ga_step_generation: null handle"); return PRL_ERR_INVALID; }
+    if (ga->mode == prl_ga::HOST_EXCHANGE) { set_error("prl_ga_step_generation: a rank of a multi-process GA exchanges through the host between prl_ga_best and prl_ga_next_generation"); return PRL_ERR_INVALID; }
+    int rc = ga->generation < 0 ? prl_ga_init(ga) : PRL_OK;
+    if (rc == PRL_OK) rc = prl_ga_best(ga, best_score, best_genome, best_index);
+    if (rc == PRL_OK) rc = prl_ga_next_generation(ga);
+    return rc;
+}
+
+int prl_ga_read_generation(prl_ga* ga, float* scores, uint8_t* genomes) {
+    if (!ga) { set_error("prl_ga_read_generation: null handle"); return PRL_ERR_INVALID; }
+    if (ga->generation < 0) { set_error("prl_ga_read_generation: call prl_ga_init first"); return PRL_ERR_INVALID; }
+    if (ga->mode == prl_ga::HOST_EXCHANGE) { set_error("prl_ga_read_generation: a rank of a multi-process GA holds the gathered generation in its prl_ga_buffers"); return PRL_ERR_INVALID; }
+    for (GaShard& s : ga->shards) {
+        DeviceGuard g(s.device);
+        if (scores) CUDA_TRY(cudaMemcpyAsync(scores + s.local_off, s.local_scores, (size_t)s.n_local * 4, cudaMemcpyDefault, s.stream));
+        if (genomes) CUDA_TRY(cudaMemcpyAsync(genomes + (size_t)s.local_off * ga->genome_len, s.genomes[s.cur], (size_t)s.n_local * ga->genome_len, cudaMemcpyDefault, s.stream));
+    }
+    for (GaShard& s : ga->shards) { DeviceGuard g(s.device); CUDA_TRY(cudaStreamSynchronize(s.stream)); }
+    return PRL_OK;
+}
+
+int64_t prl_ga_generation(const prl_ga* ga) { return ga ? (ga->generation < 0 ? 0 : ga->generation) : 0; }
+int64_t prl_ga_launch_count(const prl_ga* ga) {
+    if (!ga) return 0;
+    int64_t n = 0;
+    for (const GaShard& s : ga->shards) n += s.launches + prl_batch_launch_count(s.batch);
+    return n;
+}
 
 int64_t prl_ga_env_steps(prl_ga* ga) {
     if (!ga) return -1;
-    DeviceGuard g(ga->device);
-    if (cudaMemsetAsync(ga->steps_sum, 0, 8, ga->stream) != cudaSuccess) return -1;
-    unsigned nb = blocks_for(ga->n_local, kGaBlock);
-    if (nb > 1184) nb = 1184;
-    sum_steps_kernel<<<nb, kGaBlock, 0, ga->stream>>>(ga->batch->state + (size_t)F_STEPS * ga->batch->n, ga->n_local, ga->steps_sum);
-    ++ga->launches;
-    unsigned long long s = 0;
-    if (cudaMemcpyAsync(&s, ga->steps_sum, 8, cudaMemcpyDeviceToHost, ga->stream) != cudaSuccess) return -1;
-    if (cudaStreamSynchronize(ga->stream) != cudaSuccess) return -1;
-    return (int64_t)s;
+    unsigned long long sums[kMaxShards];
+    for (size_t k = 0; k < ga->shards.size(); ++k) {
+        GaShard& s = ga->shards[k];
+        DeviceGuard g(s.device);
+        if (cudaMemsetAsync(s.steps_sum, 0, 8, s.stream) != cudaSuccess) return -1;
+        unsigned nb = blocks_for(s.n_local, kGaBlock);
+        if (nb > 1184) nb = 1184;
+        sum_steps_kernel<<<nb, kGaBlock, 0, s.stream>>>(s.batch->state + (size_t)F_STEPS * s.batch->n, s.n_local, s.steps_sum);
+        ++s.launches;
+        if (cudaMemcpyAsync(&sums[k], s.steps_sum, 8, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess) return -1;
+    }
+    int64_t total = 0;
+    for (size_t k = 0; k < ga->shards.size(); ++k) {
+        DeviceGuard g(ga->shards[k].device);
+        if (cudaStreamSynchronize(ga->shards[k].stream) != cudaSuccess) return -1;
+        total += (int64_t)sums[k];
+    }
+    return total;
 }
 
 }  // extern "C"

@@ -70,12 +70,16 @@ extern "C" {
 
     pub fn prl_ga_create(w: *const prl_world, cfg: *const prl_ga_config, device: i32, stream: *mut c_void, rank: i32, n_ranks: i32,
                          out: *mut *mut prl_ga) -> c_int;
+    pub fn prl_ga_create_multi(w: *const prl_world, cfg: *const prl_ga_config, devices: *const i32, n_devices: i32, out: *mut *mut prl_ga) -> c_int;
     pub fn prl_ga_destroy(g: *mut prl_ga);
+    pub fn prl_ga_num_shards(g: *const prl_ga) -> i32;
     pub fn prl_ga_init(g: *mut prl_ga) -> c_int;
     pub fn prl_ga_buffers(g: *mut prl_ga, local_scores: *mut *mut f32, local_genomes: *mut *mut u8, global_scores: *mut *mut f32,
                           global_genomes: *mut *mut u8, local_count: *mut i64, local_offset: *mut i64, genome_len: *mut i32) -> c_int;
     pub fn prl_ga_best(g: *mut prl_ga, best_score: *mut f32, best_genome: *mut u8, best_index: *mut i64) -> c_int;
     pub fn prl_ga_next_generation(g: *mut prl_ga) -> c_int;
+    pub fn prl_ga_step_generation(g: *mut prl_ga, best_score: *mut f32, best_genome: *mut u8, best_index: *mut i64) -> c_int;
+    pub fn prl_ga_read_generation(g: *mut prl_ga, scores: *mut f32, genomes: *mut u8) -> c_int;
     pub fn prl_ga_generation(g: *const prl_ga) -> i64;
     pub fn prl_ga_launch_count(g: *const prl_ga) -> i64;
     pub fn prl_ga_env_steps(g: *mut prl_ga) -> i64;

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} is declared in include/prl.h but not exported by libprl.so"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS)
-    assert _lib.lib().prl_abi_version() == 1
+    assert _lib.lib().prl_abi_version() == 2
 
 
 def test_rust_facade_binds_exactly_the_exported_symbols():

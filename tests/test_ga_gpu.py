@@ -10,6 +10,7 @@ import pytest
 
 import ga_ref
 import physics_reinforcement_learning_environment_b200 as prl
+from physics_reinforcement_learning_environment_b200 import _lib
 from conftest import world_dict, world_text
 from oracle import binding as oracle
 
@@ -92,6 +93,83 @@ def test_population_sharding_does_not_change_the_result():
         single.next_generation()
         for p in ranks:
             p.next_generation()
+
+
+@pytest.mark.parametrize("keep_best", [False, True])
+def test_peer_shards_inside_the_c_abi_equal_the_unsharded_ga(keep_best):
+    """prl_ga_create_multi through ctypes only (no torch.distributed, no host exchange): one slice
+    and one stream per listed device, scores pushed into the peers' score vectors, parent genomes
+    read from the owning slice by the breeding kernel. With one visible GPU the slices all sit on
+    device 0 (the same code path: peer copies and peer pointers of a device to itself); with
+    more, one slice per GPU over NVLink. Every genome and score of every generation must equal
+    the unsharded GA's."""
+    n_dev = _lib.lib().prl_device_count()
+    devices = list(range(n_dev)) if n_dev >= 2 else [0, 0, 0]
+    if len(devices) == 2:
+        devices = [0, 1, 0]  # ragged three-way split, two slices on device 0
+    world = prl.World.from_json(world_text("push"))
+    kw = dict(number_of_steps=300, number_of_agents=1000 + 3, repeat_move=20, mutation_rate=0.1, keep_best=keep_best, seed=4242)
+    single = prl.GaPopulation(world, **kw)
+    multi = prl.GaPopulation(world, devices=devices, **kw)
+    assert multi.num_shards == len(devices) and single.num_shards == 1
+    for gen in range(4):
+        b1 = single.step_generation()
+        bm = multi.step_generation()
+        assert bits(b1[0]) == bits(bm[0]) and b1[2] == bm[2] and np.array_equal(b1[1], bm[1]), gen
+        assert single.generation == multi.generation == gen + 1
+        s1, g1 = single.read_generation()
+        sm, gm = multi.read_generation()
+        assert np.array_equal(g1, gm), gen
+        assert np.array_equal(bits(s1), bits(sm)), gen
+    # and both equal the numpy restatement of the breeding (children of the last generation)
+    assert multi.env_steps() == single.env_steps() > 0
+    with pytest.raises(prl.PrlError):
+        multi.tensors()  # no host-visible exchange buffers in this mode
+
+
+def test_single_rank_buffers_alias_and_swap():
+    """include/prl.h: with one rank local_* and global_* are the same memory (no copy per
+    generation) and hold the CURRENT generation right after init / next_generation."""
+    pop, cfg = make("jump", number_of_agents=50)
+    pop.init()
+    ls, lg, gs, gg = pop.tensors()
+    assert ls.data_ptr() == gs.data_ptr() and lg.data_ptr() == gg.data_ptr()
+    g0, s0 = lg.cpu().numpy().copy(), ls.cpu().numpy().copy()
+    assert np.array_equal(bits(s0), bits(_scores_of(g0, "jump", 200)))
+    assert np.array_equal(g0, ga_ref.init_genomes(50, 10, cfg["seed"]))
+    pop.next_generation()
+    ls2, lg2, gs2, gg2 = pop.tensors()
+    assert lg2.data_ptr() == gg2.data_ptr() and lg2.data_ptr() != lg.data_ptr()
+    ref, _ = ga_ref.breed(g0, s0, 1, cfg["seed"], cfg["mutation_rate"], False)
+    assert np.array_equal(lg2.cpu().numpy(), ref)
+
+
+def _scores_of(genomes, name, steps):
+    rs, _, _ = oracle.rollout_batch(world_dict(name), genomes, 20, steps, early_exit=True, n_threads=os.cpu_count())
+    return rs
+
+
+def test_ga_reports_contact_overflow_instead_of_selecting_on_inexact_scores():
+    """A world whose environments need more simultaneous contact manifolds than PRL_MAX_CONTACTS:
+    the scores are not exact, so prl_ga_best must fail with PRL_ERR_OVERFLOW rather than report a
+    best agent (the batch API reports the same through prl_batch_sync)."""
+    # a long plank resting on 20 posts: 20 plank-post manifolds alive at once
+    n_posts = 20
+    objs = [{"object": {"Block": {"fixed": True}}, "position": [-300.0 + 30.0 * i, -40.0, float(i + 1)], "scale": [14.0, 40.0], "rotation": 0.0}
+            for i in range(n_posts)]
+    objs.append({"object": {"Block": {"fixed": False}}, "position": [-15.0, -14.0, 30.0], "scale": [30.0 * n_posts + 20.0, 12.0], "rotation": 0.0})
+    objs.append({"object": "Goal", "position": [500.0, 30.0, 31.0], "scale": [60.0, 60.0], "rotation": 0.0})
+    world = prl.World.from_json(json.dumps({"player_position": [0.0, 24.0], "objects": objs}))
+    env = prl.BatchedEnvironment(world, 8)
+    env.step_uniform(0, 5)
+    with pytest.raises(prl.PrlError) as e:
+        env.sync()
+    assert e.value.status == _lib.PRL_ERR_OVERFLOW
+    pop = prl.GaPopulation(world, number_of_steps=40, number_of_agents=16, repeat_move=20)
+    pop.init()
+    with pytest.raises(prl.PrlError) as e:
+        pop.best()
+    assert e.value.status == _lib.PRL_ERR_OVERFLOW
 
 
 def test_selection_crossover_mutation_statistics():

@@ -169,23 +169,65 @@ def test_result_is_independent_of_batch_size_and_neighbours():
     assert np.array_equal(bits(s_full[lo:hi]), bits(s_part)) and np.array_equal(w_full[lo:hi], w_part)
 
 
-def test_full_size_properties_push_65536x2000():
-    """BASELINE config C3 at full size: properties that need no oracle run of the whole batch --
-    duplicated genomes give identical results wherever they sit, every score is a finite
-    non-negative pixel distance, winners have score 0 -- plus an oracle check of a 64-env sample."""
+def test_full_size_push_65536x2000_every_env_matches_oracle():
+    """BASELINE config C3 at full size, i.e. the kernel variant bench.py times
+    (`rollout_kernel<2, DevWorldSmall, 448>`: one 448-thread block per SM, barrier every step,
+    regrouping through HBM every 128 steps): ALL 65536 environments are compared with the oracle
+    bit for bit (score, step of win), plus the size-independent properties."""
     n, L, repeat, steps = 65536, 100, 20, 2000
     genomes = random_genomes(n, L, 0xB200)
-    genomes[n // 2:] = genomes[:n // 2]
     env = prl.BatchedEnvironment(prl.World.from_json(world_text("push")), n)
     score, win = env.rollout(genomes, repeat, steps, early_exit=False)
     env.sync()
-    assert np.array_equal(bits(score[:n // 2]), bits(score[n // 2:])) and np.array_equal(win[:n // 2], win[n // 2:])
     assert np.isfinite(score).all() and (score >= 0).all()
     assert np.all(score[win > 0] == 0.0) and np.all(win[score > 0] == -1)
-    idx = np.arange(0, n // 2, n // 128)[:64]
-    rs, rw, _ = oracle.rollout_batch(world_dict("push"), np.ascontiguousarray(genomes[idx]), repeat, steps, False,
+    rs, rw, rsteps = oracle.rollout_batch(world_dict("push"), genomes, repeat, steps, False, n_threads=os.cpu_count())
+    assert rsteps == n * steps
+    bad = np.flatnonzero((bits(score) != bits(rs)) | (win != rw))
+    assert bad.size == 0, f"{bad.size} of {n} environments differ from the oracle, first {bad[:8]}"
+    # the GA's break-on-win semantics through the same kernel variant
+    score, win = env.rollout(genomes, repeat, steps, early_exit=True)
+    _, _, run = env.rollout_info()
+    env.sync()
+    rs, rw, rsteps = oracle.rollout_batch(world_dict("push"), genomes, repeat, steps, True, n_threads=os.cpu_count())
+    assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw) and int(run.sum()) == rsteps
+
+
+def test_ragged_batch_on_the_448_thread_kernel():
+    """The smallest batches that take the 448-thread variant, with a ragged tail (the last block is
+    partly empty and its idle lanes still take part in the votes, barriers and regrouping)."""
+    sm = 148
+    n = sm * 448 // 2 + 17  # 33152 + 17
+    L, repeat, steps = 30, 20, 600
+    distinct = 4096 + 17
+    genomes = random_genomes(distinct, L, 0x448)
+    genomes = np.ascontiguousarray(np.resize(genomes, (n, L)))  # rows repeat with period `distinct`
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text("push")), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    env.sync()
+    rs, rw, _ = oracle.rollout_batch(world_dict("push"), np.ascontiguousarray(genomes[:distinct]), repeat, steps, False,
                                      n_threads=os.cpu_count())
-    assert np.array_equal(bits(score[idx]), bits(rs)) and np.array_equal(win[idx], rw)
+    idx = np.arange(n) % distinct
+    assert np.array_equal(bits(score), bits(rs[idx])) and np.array_equal(win, rw[idx])
+
+
+@pytest.mark.parametrize("which", ["stack", "posts8", "posts6"])
+def test_448_thread_kernel_variants_with_several_pushable_blocks(which):
+    """`rollout_kernel<MAXB, DevWorldSmall, 448>` (a pile of three pushable blocks) and
+    `rollout_kernel<MAXB, DevWorld, 448>` (a plank on 8 posts: 17+ candidate pairs, the general
+    tables) are only launched for batches of >= 33152 environments; 6 posts is push's own variant
+    solving in rounds. Every environment is compared with the oracle (4096 distinct genomes)."""
+    world = {"stack": edge_case_worlds()["stack"], "posts8": many_supports_world(8), "posts6": many_supports_world(6)}[which]
+    n, L, repeat, steps = 148 * 448 // 2 + 448, 20, 20, 400
+    distinct = 4096
+    genomes = np.ascontiguousarray(np.resize(random_genomes(distinct, L, 0x99 + len(which)), (n, L)))
+    env = prl.BatchedEnvironment(prl.World.from_json(json.dumps(world)), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    env.sync()
+    rs, rw, _ = oracle.rollout_batch(world, np.ascontiguousarray(genomes[:distinct]), repeat, steps, False, n_threads=os.cpu_count())
+    idx = np.arange(n) % distinct
+    bad = np.flatnonzero((bits(score) != bits(rs[idx])) | (win != rw[idx]))
+    assert bad.size == 0, f"{bad.size} of {n} environments differ from the oracle, first {bad[:8]}"
 
 
 def test_reset_and_device_buffers():
