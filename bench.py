@@ -24,6 +24,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+def workload_config(args, genome_len):
+    """`config` of the JSON line: identical for the CUDA arm and the --impl reference arm."""
+    return {"workload": f"{args.world}.json, {args.envs} envs x {args.horizon} steps per GPU, genome_len {genome_len}, "
+                        f"repeat_move {args.repeat}, early exit off",
+            "l2": "CUDA arm: L2 flushed between timed passes (256 MB fill outside the event brackets); CPU arm: not applicable"}
+
+
+def kernel_source_hash():
+    """sha256 over the sources the rollout kernel is compiled from (device code, world tables, libm,
+    build flags): keys the committed ncu figures (profiles/rollout_profile.json) to the kernel they
+    were measured on."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "physics_reinforcement_learning_environment_b200", "csrc")
+    for f in ("prl_device.cuh", "prl_kernels.cuh", "prl_world.h", "prl_libm.h", "Makefile"):
+        h.update(f.encode())
+        h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def algorithmic_bytes(n_bodies):
     """algorithmic HBM bytes per env-step: cross-step body state read once + written once"""
     return 2 * (28 + 32 * (n_bodies - 1))
@@ -116,8 +136,7 @@ def run_reference(args, world_text, rank):
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_time / max(1, args.steps),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.world}.json, {args.envs} envs x {args.horizon} steps per GPU, genome_len {genome_len}, repeat_move {args.repeat}, early exit off",
-                   "l2": "n/a (CPU)"},
+        "config": workload_config(args, genome_len),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -137,6 +156,9 @@ def main():
     ap.add_argument("--repeat", type=int, default=20)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C4 records")
+    ap.add_argument("--no-ga", action="store_true", help="skip the GA (C5-shape) record")
+    ap.add_argument("--ga-agents", type=int, default=131072, help="GA agents per GPU")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,6 +244,8 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    env.sync()  # raises PRL_ERR_OVERFLOW if an environment ran out of contact-manifold slots in the timed passes
+
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -231,52 +255,188 @@ def main():
     total_steps = env_steps_per_pass * args.steps * world_size
     value = total_steps / (dev_ms * 1e-3)
     e2e_value = total_steps / (e2e_ms * 1e-3)
+    del env, flush
+
+    secondary = None if args.no_secondary else secondary_records(prl, torch, dist, dev, local_rank, world_size, stream)
+    ga = None if args.no_ga else ga_record(prl, torch, dist, dev, local_rank, rank, world_size, args)
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured"
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst copy bandwidth)"
         else:
-            peak, peak_src = 6650.0, "fallback"
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         balg = algorithmic_bytes(n_bodies)
         launch_s = dev_ms * 1e-3 / args.steps
         achieved = balg * env_steps_per_pass / launch_s / 1e9
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
-        if os.path.exists(tpath):
+        # ncu figures of the dominant kernel come from the committed capture of THIS kernel source
+        # (profiles/rollout_profile.json, keyed by the source hash); a stale capture is not reported
+        traffic, issue, src_hash = None, None, kernel_source_hash()
+        ppath = os.path.join(ROOT, "profiles", "rollout_profile.json")
+        if os.path.exists(ppath):
             try:
-                tj = json.load(open(tpath))
-                if tj.get("envs") == args.envs and tj.get("horizon") == args.horizon and tj.get("world") == args.world:
-                    traffic = tj.get("bytes_per_launch")
+                pj = json.load(open(ppath))
+                same = pj.get("envs") == args.envs and pj.get("horizon") == args.horizon and pj.get("world") == args.world
+                if same and pj.get("source_sha256") == src_hash:
+                    traffic = pj.get("dram_bytes_per_launch")
+                    wi = pj.get("warp_instructions_per_launch")
+                    issue = {"warp_inst_per_env_step": wi / env_steps_per_pass if wi else None,
+                             "issue_frac": pj.get("issue_active_frac"), "active_lanes": pj.get("active_lanes_per_inst"),
+                             "source": pj.get("source")}
+                elif same:
+                    issue = {"stale": f"profiles/rollout_profile.json was captured on kernel source {pj.get('source_sha256')}, this run is {src_hash}"}
             except Exception:
-                traffic = None
+                traffic, issue = None, None
         cpu = None
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             # bounded sample: ~cpu-seconds of host work at ~3 us per env-step per core
             sample_envs = int(max(cores, min(args.envs, args.cpu_seconds * cores / (3.0e-6 * args.horizon))))
-            rate, s, dt = cpu_reference_rate(world_text, sample_envs, genome_len, args.repeat, args.horizon, cores, 0xB200)
+            rate, s_, dt = cpu_reference_rate(world_text, sample_envs, genome_len, args.repeat, args.horizon, cores, 0xB200)
             cpu = {"value": rate, "unit": "env-steps/s", "cores": cores, "kind": "port",
                    "sample": f"first {sample_envs} envs x {args.horizon} steps of the same workload, {cores} threads, {dt:.1f} s"}
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.world}.json, {args.envs} envs x {args.horizon} steps per GPU, genome_len {genome_len}, repeat_move {args.repeat}, early exit off",
-                       "l2": "flushed between timed passes (256 MB fill outside the event brackets)",
-                       "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps},
+            "config": workload_config(args, genome_len),
+            "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,
-                         "note": "state stays in registers across the fused horizon, so the kernel is issue-bound, not HBM-bound (DESIGN.md)"},
+                         "issue": issue, "kernel_source_sha256": src_hash,
+                         "note": "state stays in registers across the fused horizon, so the kernel is issue-bound, not HBM-bound (DESIGN.md): `issue` is the binding roof"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(args.envs * genome_len),
                     "d2h_bytes_per_step": int(args.envs * 8)},
             "gpu_launches": int(gpu_launches),
             "clocks": clocks,
+            "secondary": secondary,
+            "ga": ga,
         }
         print(json.dumps(line), flush=True)
     if world_size > 1:
         dist.destroy_process_group()
+
+
+def _timed_pass(torch, stream, fn, flush, reps=3):
+    """best-of-`reps` device time (ms) of fn() after one warm-up, L2 flushed before every pass"""
+    fn()
+    best = None
+    for k in range(reps):
+        flush.fill_(k)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+def secondary_records(prl, torch, dist, dev, local_rank, world_size, stream):
+    """The other single-GPU configurations of BASELINE.json, one fused rollout each (device time,
+    early exit off, inputs resident): C2 = jump.json 4096 x 1000, C4 = synthetic 64-obstacle world,
+    131072 envs per GPU x 1000 (1M envs over 8 GPUs). Whole-job env-steps/s, max over ranks."""
+    out = {}
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    for key, wname, n, horizon in (("C2_jump_4096x1000", "jump", 4096, 1000), ("C4_synth64_131072x1000_per_gpu", "synth64", 131072, 1000)):
+        world = prl.World.from_json(open(os.path.join(ROOT, "worlds", f"{wname}.json")).read())
+        env = prl.BatchedEnvironment(world, n, device=local_rank, stream=stream.cuda_stream)
+        genomes = torch.from_numpy(make_genomes(n, horizon // 20, 0xB200 + local_rank)).to(dev)
+        score = torch.empty(n, dtype=torch.float32, device=dev)
+        win = torch.empty(n, dtype=torch.int32, device=dev)
+        ms = _timed_pass(torch, stream, lambda: env.rollout(genomes, 20, horizon, early_exit=False, out_score=score, out_step_of_win=win), flush)
+        env.sync()
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world_size > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        out[key] = {"value": n * horizon * world_size / (ms * 1e-3), "unit": "env-steps/s", "ms": ms, "n_gpus": world_size,
+                    "roofline_frac": algorithmic_bytes(world.counts()[0]) * n * horizon / (ms * 1e-3) / 1e9 / 6551.7}
+        del env
+    return out
+
+
+def ga_record(prl, torch, dist, dev, local_rank, rank, world_size, args):
+    """BASELINE config C5 shape: the full GA (main.rs:41-163) on push.json, 131072 agents per GPU,
+    2000 steps, 3 generations. N > 1: one process per GPU, the generation all-gathered with NCCL once
+    per generation, and rank 0's gathered generations compared bit for bit with an unsharded run of
+    the same seed on its own GPU. N == 1: the same comparison for the in-library peer shards
+    (prl_ga_create_multi) against the unsharded population."""
+    world = prl.World.from_json(open(os.path.join(ROOT, "worlds", "push.json")).read())
+    per_gpu, gens = args.ga_agents, 3
+    kw = dict(number_of_steps=2000, number_of_agents=per_gpu * world_size, repeat_move=20, mutation_rate=0.1, keep_best=False, seed=0xC5)
+    stream = torch.cuda.current_stream()
+    pop = prl.GaPopulation(world, device=local_rank, stream=stream.cuda_stream, rank=rank, n_ranks=world_size, **kw)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4 * gens)]
+    gathered = []
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    pop.init()
+    env_steps = 0
+    for g in range(gens):
+        ev[4 * g].record(stream)
+        pop.gather()
+        ev[4 * g + 1].record(stream)
+        best = pop.best()
+        if rank == 0:
+            _, _, gs, gg = pop.tensors()
+            gathered.append((gs.clone(), gg.clone(), best))
+        env_steps += pop.env_steps()
+        if g + 1 < gens:
+            pop.next_generation()
+    torch.cuda.synchronize()
+    if world_size > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    ag_ms = sum(ev[4 * g].elapsed_time(ev[4 * g + 1]) for g in range(gens)) / gens
+    t = torch.tensor([wall * 1e3 / gens, ag_ms, float(env_steps)], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        mx = t.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        gen_ms, ag_ms, steps_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        gen_ms, ag_ms, steps_total = float(t[0]), float(t[1]), float(t[2])
+    launches = pop.launch_count
+    pop.close()
+    rec = None
+    if rank == 0:
+        n_total, L = kw["number_of_agents"], 2000 // 20
+        equal = True
+        if world_size > 1:
+            single = prl.GaPopulation(world, device=local_rank, **kw)
+            single.init()
+            for g in range(gens):
+                b1 = single.best()
+                s1, g1 = single.read_generation()
+                gs, gg, bm = gathered[g]
+                equal &= bool(np.array_equal(gs.cpu().numpy().view(np.uint32), s1.view(np.uint32)) and np.array_equal(gg.cpu().numpy(), g1))
+                equal &= bool(np.float32(b1[0]).view(np.uint32) == np.float32(bm[0]).view(np.uint32) and b1[2] == bm[2])
+                if g + 1 < gens:
+                    single.next_generation()
+            single.close()
+            how = f"rank 0's NCCL-gathered generations 0..{gens - 1} ({n_total} agents) == unsharded run of the same seed on one GPU, scores and genomes bit for bit"
+        else:
+            small = dict(kw, number_of_agents=16384 + 5)
+            single, multi = prl.GaPopulation(world, device=local_rank, **small), prl.GaPopulation(world, devices=[local_rank] * 3, **small)
+            for g in range(gens):
+                b1, bm = single.step_generation(), multi.step_generation()
+                (s1, g1), (s2, g2) = single.read_generation(), multi.read_generation()
+                equal &= bool(np.array_equal(s1.view(np.uint32), s2.view(np.uint32)) and np.array_equal(g1, g2) and b1[2] == bm[2])
+            single.close(); multi.close()
+            how = f"prl_ga_create_multi with 3 peer shards on the one GPU == unsharded, {small['number_of_agents']} agents x {gens} generations, bit for bit"
+        rec = {"workload": f"push.json GA, {per_gpu} agents per GPU ({n_total} total) x 2000 steps, repeat_move 20, mutation 0.1, {gens} generations, early exit on win",
+               "gen_ms": gen_ms, "allgather_ms": ag_ms if world_size > 1 else 0.0,
+               "bytes": int(n_total * (L + 4)) if world_size > 1 else 0,
+               "env_steps_per_s": steps_total / (gen_ms * 1e-3 * gens), "n_ranks": world_size,
+               "exchange": "ncclAllGather (torch.distributed) of scores + genomes on the GA's stream" if world_size > 1 else "none (one GPU)",
+               "sharded_equals_unsharded": bool(equal), "check": how, "gpu_launches": int(launches)}
+    return rec
 
 
 if __name__ == "__main__":

@@ -49,6 +49,14 @@
 #define PRL_TICK(i) do { } while (0)
 #endif
 
+// PRL_HOST_TRACE (tests/hostsim only): per-step work counters for offline studies of how
+// environments should be grouped into warps
+#if defined(PRL_HOST_TRACE)
+#define PRL_TRACE(stmt) do { stmt; } while (0)
+#else
+#define PRL_TRACE(stmt) do { } while (0)
+#endif
+
 namespace prl {
 
 PRL_D int first_zero_bit(uint32_t used) {  // index of the lowest clear bit, 32 if none
@@ -537,6 +545,9 @@ struct Stepper {
     int gs_b[2];
 #if defined(PRL_PHASE_TIMING)
     long long tacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tlast = 0;
+#endif
+#if defined(PRL_HOST_TRACE)
+    int tr_cand = 0, tr_full = 0;  // narrow-phase pairs visited / recomputed from scratch by the last detection
 #endif
     PRL_D Stepper(const WT& w, E& env, Contacts<S>& contacts, void* warp_pool)
         : W(w), e(env), k(contacts), pool(static_cast<unsigned char*>(warp_pool)), ent0(0), stride(1), cfm_reg(w.cfm_factor), active(0), cons(0), cm_tb(0), cm_gr(0), ncons(0), need(0), ntb(0),
@@ -1345,8 +1356,10 @@ struct Stepper {
             // for both, only the out-of-line recompute differs. (Two loops doubled the hot code and
             // ran max(player pairs) + max(block pairs) trips per warp instead of max(pairs).)
             const int npp = W.n_player_pairs;
+            PRL_TRACE(tr_cand = 0; tr_full = 0);
 #pragma unroll 1
             for (uint32_t m_ = cand; m_ != 0; m_ &= m_ - 1) {
+                PRL_TRACE(++tr_cand);
                 const int p = first_bit_from(m_, 0);
                 const uint32_t info = W.pair_info[p];
                 const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
@@ -1356,6 +1369,7 @@ struct Stepper {
                 const Iso pose1 = pair_collider_pose(p, info_b1(info));
                 const Iso pos12 = inv_mul(pose1, pair_collider_pose(p, info_b2(info)));
                 if (!manifold_try_update(m, pos12)) {
+                    PRL_TRACE(++tr_full);
                     if (NB == 1 || p < npp) m = contact_capsule_cuboid_full(pos12, W.radius, W.half_height, V(he.z, he.w), W.prediction);
                     else m = contact_cuboid_cuboid_full(pos12, V(he.x, he.y), V(he.z, he.w), W.prediction);
                 }

@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     const int main_steps = genome_len * repeat_move;
     const int total = main_steps + number_of_steps % repeat_move;
     int g = 0, rep = 0, t = 0, iter = 0;
+#if defined(PRL_REGROUP_AVG)
+    int acc_need = 0;
+#endif
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
     int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes + Sim::kPoolPad);  // only if BLOCK == kBigBlock
 #if defined(PRL_PHASE_TIMING)
@@ -344,6 +347,21 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
         const bool all_done = __syncthreads_and(!(t < total));
         PRL_TICK_K(8);
         if (all_done) break;
+#if defined(PRL_ICACHE_PAD)
+        {
+            // measurement builds only: PRL_ICACHE_PAD KB of straight-line code executed once per step, to
+            // measure what a KB of per-step instruction footprint costs (profiles/r02_icache_pad.md)
+            float p0 = score, p1 = score, p2 = score, p3 = score;
+#pragma unroll
+            for (int q = 0; q < PRL_ICACHE_PAD * 16; ++q) {
+                asm volatile("add.f32 %0, %0, 0f3F800000;" : "+f"(p0));
+                asm volatile("add.f32 %0, %0, 0f3F800000;" : "+f"(p1));
+                asm volatile("add.f32 %0, %0, 0f3F800000;" : "+f"(p2));
+                asm volatile("add.f32 %0, %0, 0f3F800000;" : "+f"(p3));
+            }
+            if (p0 + p1 + p2 + p3 == -12345.0f) score = p0;
+        }
+#endif
         if (BLOCK == kBigBlock && PRL_UNLIKELY(iter > 0 && iter % kRegroupEvery == 0)) {
             // ---- regroup: park, sort, pick up (all threads of the block are here, nothing pending)
             int* hist = regroup;
@@ -356,7 +374,13 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
                 st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
                 st[(int64_t)F_ROLL * n + i] = (uint32_t)t;
             }
+#if defined(PRL_REGROUP_AVG)
+            const int avg2 = (2 * acc_need + kRegroupEvery / 2) / kRegroupEvery;  // twice the mean rows per step since the last regroup
+            const int key = t < total ? 1 + (avg2 < 32 ? avg2 : 32) : 0;
+            acc_need = 0;
+#else
             const int key = t < total ? 1 + (sim.need < 32 ? sim.need : 32) : 0;
+#endif
             if (threadIdx.x < kRegroupKeys) hist[threadIdx.x] = 0;
             __syncthreads();
             const int pos = atomicAdd(&hist[key], 1);
@@ -385,6 +409,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
         const bool run = t < total;
         const bool in_genes = t < main_steps;
         const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
+#if defined(PRL_REGROUP_AVG)
+        acc_need += need;
+#endif
         solve_in_rounds<Sim>(run, need, [&](int entry, int stride) {
             float d = sim.finish_step(entry, stride);
             ++steps;

@@ -18,7 +18,18 @@ extern "C" void hs_need_hist(long* out, int reset) {
     memcpy(out, g_need_hist, sizeof g_need_hist);
     if (reset) memset(g_need_hist, 0, sizeof g_need_hist);
 }
+// optional per-step trace (offline grouping studies, scripts/regroup_study.py): 4 ints per step --
+// solver rows, narrow-phase pairs visited / recomputed by the detection that preceded the step,
+// sleeping mask
+static int* g_trace = nullptr;
+static long g_trace_cap = 0, g_trace_len = 0;
+extern "C" void hs_set_trace(int* buf, long cap_steps) { g_trace = buf; g_trace_cap = cap_steps; g_trace_len = 0; }
+extern "C" long hs_trace_len() { return g_trace_len; }
 template <class SIM> static void count_need(const SIM& sim) {
+    if (g_trace && g_trace_len < g_trace_cap) {
+        int* o = g_trace + 4 * g_trace_len++;
+        o[0] = sim.need; o[1] = sim.tr_cand; o[2] = sim.tr_full; o[3] = (int)sim.e.sleeping;
+    }
     ++g_need_hist[0][sim.need < 39 ? sim.need : 39];
     ++g_need_hist[1][sim.ntb < 39 ? sim.ntb : 39];
     int live = sim.live_count();

@@ -23,11 +23,22 @@ python $ROOT/tools/ncu_regions.py $TMP/src.csv rollout_kernelILi2 $TMP/prl_api.s
 echo '```'
 } > $OUT
 python - "$OUT" "$ROOT" <<'PY'
+# the ncu figures bench.py reports in `roofline` (traffic, issue), keyed by the kernel source hash
 import re,json,sys
+sys.path.insert(0, sys.argv[2])
+import bench
 s=open(sys.argv[1]).read()
 mul={'Gbyte':1e9,'Mbyte':1e6,'Kbyte':1e3,'byte':1}
 m1=re.search(r'dram__bytes_read.sum,(\w+),([\d.]+)',s); m2=re.search(r'dram__bytes_write.sum,(\w+),([\d.]+)',s)
 tot=float(m1.group(2))*mul[m1.group(1)]+float(m2.group(2))*mul[m2.group(1)]
-json.dump({"world":"push","envs":65536,"horizon":2000,"bytes_per_launch":tot,"source":sys.argv[1].split('/')[-1]+" (dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture)"},open(sys.argv[2]+'/profiles/dram_traffic.json','w'),indent=1)
-print(tot/1e9,'GB DRAM traffic per launch')
+val=lambda name: float(re.search(name+r',[^,]*,([\d.]+)',s).group(1))
+rec={"world":"push","envs":65536,"horizon":2000,"source_sha256":bench.kernel_source_hash(),
+     "dram_bytes_per_launch":tot,
+     "warp_instructions_per_launch":val('smsp__inst_executed.sum'),
+     "issue_active_frac":val('smsp__issue_active.avg.pct_of_peak_sustained_active')/100.0,
+     "active_lanes_per_inst":val('smsp__thread_inst_executed_per_inst_executed.ratio'),
+     "kernel_ms_under_ncu":val('gpu__time_duration.sum'),
+     "source":"profiles/"+sys.argv[1].split('/')[-1]+" (one ncu --set full capture of the rollout kernel)"}
+json.dump(rec,open(sys.argv[2]+'/profiles/rollout_profile.json','w'),indent=1)
+print(rec)
 PY

@@ -31,4 +31,5 @@ def main():
     print(f"{'function':44s} {'samp%':>6s} {'inst%':>6s} {'lanes':>5s} {'sass':>5s}")
     for k,a in sorted(agg.items(), key=lambda kv:-kv[1]['inst'])[:40]:
         print(f"{k[0][:14]+':'+k[1]:44s} {100*a['samples']/ts:6.2f} {100*a['inst']/ti:6.2f} {a['tinst']/max(1,a['inst']):5.1f} {a['sass']:5d}")
-main()
+if __name__ == "__main__":
+    main()
