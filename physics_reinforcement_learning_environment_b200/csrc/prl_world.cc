@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <cmath>
 
 #include <charconv>
 
@@ -205,49 +206,168 @@ int build_dev_world(prl_world* w) {
 }
 
 // ---------------------------------------------------------------------------- JSON
+// serde_json::from_str::<World> (editor.rs:916-936) with #[derive(Deserialize)] on World,
+// ObjectAndTransform and WorldObject (common.rs:19-49), restated:
+//  * RFC 8259 grammar, whitespace = space \t \n \r, nothing but whitespace after the value,
+//    nesting limit 128 (serde_json's recursion limit);
+//  * a struct is a map or a sequence of its fields in declaration order; in a map unknown keys
+//    are IGNORED (their value may be any JSON value: no deny_unknown_fields), a known key
+//    twice is an error, a missing field is an error; keys are compared after unescaping;
+//  * [f32; N] is a sequence of exactly N numbers; a number is parsed as f64 and narrowed with
+//    `as f32` (integers are accepted; a literal that overflows f64 is an error);
+//  * the externally tagged enum: "Goal" | {"Goal":null} | {"Block":{"fixed":b}} | {"Block":[b]};
+//    a map tag has exactly one key.
 namespace {
 struct Cur {
     const char* p;
     const char* e;
     void ws() { while (p < e && (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r')) ++p; }
+    bool peek(char c) { ws(); return p < e && *p == c; }
     bool eat(char c) { ws(); if (p < e && *p == c) { ++p; return true; } return false; }
-    bool key(std::string* out) {
+    bool lit(const char* w) {
+        size_t n = strlen(w);
+        if ((size_t)(e - p) >= n && !strncmp(p, w, n)) { p += n; return true; }
+        return false;
+    }
+    static void utf8(std::string* out, unsigned cp) {
+        if (cp < 0x80) out->push_back((char)cp);
+        else if (cp < 0x800) { out->push_back((char)(0xC0 | (cp >> 6))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+        else if (cp < 0x10000) { out->push_back((char)(0xE0 | (cp >> 12))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+        else { out->push_back((char)(0xF0 | (cp >> 18))); out->push_back((char)(0x80 | ((cp >> 12) & 0x3F))); out->push_back((char)(0x80 | ((cp >> 6) & 0x3F))); out->push_back((char)(0x80 | (cp & 0x3F))); }
+    }
+    bool hex4(unsigned* v) {
+        if (e - p < 4) return false;
+        unsigned r = 0;
+        for (int i = 0; i < 4; ++i) {
+            char ch = p[i];
+            unsigned d = ch >= '0' && ch <= '9' ? ch - '0' : ch >= 'a' && ch <= 'f' ? ch - 'a' + 10 : ch >= 'A' && ch <= 'F' ? ch - 'A' + 10 : 99;
+            if (d == 99) return false;
+            r = r * 16 + d;
+        }
+        p += 4;
+        *v = r;
+        return true;
+    }
+    // a JSON string, unescaped; the input must be valid UTF-8 (from_str takes a &str)
+    bool str(std::string* out) {
         ws();
         if (p >= e || *p != '"') return false;
         ++p;
         out->clear();
-        while (p < e && *p != '"') {
-            if (*p == '\\') return false;  // the schema's keys and tags contain no escapes
-            out->push_back(*p++);
+        while (p < e) {
+            unsigned char ch = (unsigned char)*p;
+            if (ch == '"') { ++p; return true; }
+            if (ch < 0x20) return false;  // control characters must be escaped
+            if (ch == '\\') {
+                ++p;
+                if (p >= e) return false;
+                char c2 = *p++;
+                switch (c2) {
+                    case '"': out->push_back('"'); break;
+                    case '\\': out->push_back('\\'); break;
+                    case '/': out->push_back('/'); break;
+                    case 'b': out->push_back('\b'); break;
+                    case 'f': out->push_back('\f'); break;
+                    case 'n': out->push_back('\n'); break;
+                    case 'r': out->push_back('\r'); break;
+                    case 't': out->push_back('\t'); break;
+                    case 'u': {
+                        unsigned cp;
+                        if (!hex4(&cp)) return false;
+                        if (cp >= 0xDC00 && cp <= 0xDFFF) return false;  // lone trailing surrogate
+                        if (cp >= 0xD800 && cp <= 0xDBFF) {
+                            unsigned lo;
+                            if (e - p < 2 || p[0] != '\\' || p[1] != 'u') return false;
+                            p += 2;
+                            if (!hex4(&lo) || lo < 0xDC00 || lo > 0xDFFF) return false;
+                            cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                        }
+                        utf8(out, cp);
+                        break;
+                    }
+                    default: return false;
+                }
+                continue;
+            }
+            if (ch < 0x80) { out->push_back((char)ch); ++p; continue; }
+            // multi-byte UTF-8 sequence: validate (no overlongs, no surrogates, <= U+10FFFF)
+            int n = ch >= 0xF0 ? 4 : ch >= 0xE0 ? 3 : ch >= 0xC2 ? 2 : 0;
+            if (n == 0 || ch > 0xF4 || e - p < n) return false;
+            unsigned cp = ch & (0xFF >> (n + 1));
+            for (int i = 1; i < n; ++i) {
+                unsigned char cc = (unsigned char)p[i];
+                if ((cc & 0xC0) != 0x80) return false;
+                cp = (cp << 6) | (cc & 0x3F);
+            }
+            if ((n == 3 && cp < 0x800) || (n == 4 && cp < 0x10000) || cp > 0x10FFFF || (cp >= 0xD800 && cp <= 0xDFFF)) return false;
+            out->append(p, (size_t)n);
+            p += n;
         }
-        if (p >= e) return false;
-        ++p;
-        return true;
+        return false;
     }
+    // RFC 8259 number; serde_json: f64 parse, then `as f32`
     bool num(float* out) {
         ws();
-        const char* s = p;
+        const char* s0 = p;
         if (p < e && *p == '-') ++p;
-        bool digits = false;
-        while (p < e && *p >= '0' && *p <= '9') { ++p; digits = true; }
-        if (p < e && *p == '.') { ++p; while (p < e && *p >= '0' && *p <= '9') { ++p; digits = true; } }
-        if (digits && p < e && (*p == 'e' || *p == 'E')) {
+        if (p >= e) return false;
+        if (*p == '0') ++p;
+        else if (*p >= '1' && *p <= '9') { while (p < e && *p >= '0' && *p <= '9') ++p; }
+        else return false;
+        if (p < e && *p == '.') {
             ++p;
-            if (p < e && (*p == '+' || *p == '-')) ++p;
+            if (p >= e || *p < '0' || *p > '9') return false;
             while (p < e && *p >= '0' && *p <= '9') ++p;
         }
-        if (!digits) return false;
-        std::string tmp(s, p);
-        *out = (float)strtod(tmp.c_str(), nullptr);  // serde_json: f64 parse, then `as f32`
+        if (p < e && (*p == 'e' || *p == 'E')) {
+            ++p;
+            if (p < e && (*p == '+' || *p == '-')) ++p;
+            if (p >= e || *p < '0' || *p > '9') return false;
+            while (p < e && *p >= '0' && *p <= '9') ++p;
+        }
+        std::string tmp(s0, p);
+        double d = strtod(tmp.c_str(), nullptr);
+        if (std::isinf(d)) return false;  // serde_json: "number out of range"
+        if (out) *out = (float)d;         // `as f32`: rounds to nearest, saturates to +-inf
         return true;
     }
     bool boolean(bool* out) {
         ws();
-        if (e - p >= 4 && !strncmp(p, "true", 4)) { p += 4; *out = true; return true; }
-        if (e - p >= 5 && !strncmp(p, "false", 5)) { p += 5; *out = false; return true; }
+        if (lit("true")) { *out = true; return true; }
+        if (lit("false")) { *out = false; return true; }
         return false;
     }
-    bool farray(float* out, int n) {
+    // serde::de::IgnoredAny: any JSON value, validated and dropped
+    bool skip(int depth) {
+        ws();
+        if (p >= e || depth > 128) return false;
+        char ch = *p;
+        if (ch == '"') { std::string t; return str(&t); }
+        if (ch == 't') return lit("true");
+        if (ch == 'f') return lit("false");
+        if (ch == 'n') return lit("null");
+        if (ch == '[') {
+            ++p;
+            if (eat(']')) return true;
+            for (;;) {
+                if (!skip(depth + 1)) return false;
+                if (eat(',')) continue;
+                return eat(']');
+            }
+        }
+        if (ch == '{') {
+            ++p;
+            if (eat('}')) return true;
+            for (;;) {
+                std::string k;
+                if (!str(&k) || !eat(':') || !skip(depth + 1)) return false;
+                if (eat(',')) continue;
+                return eat('}');
+            }
+        }
+        return num(nullptr);
+    }
+    bool farray(float* out, int n) {  // [f32; n]
         if (!eat('[')) return false;
         for (int i = 0; i < n; ++i) {
             if (i && !eat(',')) return false;
@@ -257,79 +377,96 @@ struct Cur {
     }
 };
 
-bool parse_object_tag(Cur& c, int* kind) {
-    c.ws();
-    std::string k;
-    if (c.p < c.e && *c.p == '"') {  // unit variant: "Goal"
-        if (!c.key(&k) || k != "Goal") return false;
+// a struct as a map (unknown keys ignored, duplicates and missing fields are errors) or as a
+// sequence of its fields in order. field(i) parses the value of field i.
+template <class F>
+bool parse_struct(Cur& c, const char* const* names, int n, F&& field) {
+    if (c.eat('[')) {
+        for (int i = 0; i < n; ++i) {
+            if (i && !c.eat(',')) return false;
+            if (!field(i)) return false;
+        }
+        return c.eat(']');
+    }
+    if (!c.eat('{')) return false;
+    unsigned seen = 0;
+    if (!c.eat('}')) {
+        for (;;) {
+            std::string k;
+            if (!c.str(&k) || !c.eat(':')) return false;
+            int f = -1;
+            for (int i = 0; i < n; ++i) if (k == names[i]) f = i;
+            if (f < 0) { if (!c.skip(1)) return false; }
+            else {
+                if (seen & (1u << f)) return false;  // duplicate field
+                if (!field(f)) return false;
+                seen |= 1u << f;
+            }
+            if (c.eat(',')) continue;
+            if (c.eat('}')) break;
+            return false;
+        }
+    }
+    return seen == (1u << n) - 1u;  // missing field
+}
+
+// WorldObject (common.rs:46-49), externally tagged
+bool parse_world_object(Cur& c, int* kind) {
+    std::string tag;
+    if (c.peek('"')) {  // a bare string names a unit variant
+        if (!c.str(&tag) || tag != "Goal") return false;
         *kind = 2;
         return true;
     }
-    // struct variant: {"Block":{"fixed":bool}}
-    if (!c.eat('{') || !c.key(&k) || k != "Block" || !c.eat(':') || !c.eat('{')) return false;
-    if (!c.key(&k) || k != "fixed" || !c.eat(':')) return false;
-    bool fixed;
-    if (!c.boolean(&fixed)) return false;
-    if (!c.eat('}') || !c.eat('}')) return false;
-    *kind = fixed ? 0 : 1;
-    return true;
+    if (!c.eat('{') || !c.str(&tag) || !c.eat(':')) return false;
+    if (tag == "Goal") {
+        c.ws();
+        if (!c.lit("null")) return false;
+        *kind = 2;
+    } else if (tag == "Block") {
+        bool fixed = false;
+        static const char* const names[] = {"fixed"};
+        if (!parse_struct(c, names, 1, [&](int) { return c.boolean(&fixed); })) return false;
+        *kind = fixed ? 0 : 1;
+    } else {
+        return false;  // unknown variant
+    }
+    return c.eat('}');  // exactly one key
 }
 
+// ObjectAndTransform (common.rs:26-31)
 bool parse_object(Cur& c, prl_object* o) {
-    if (!c.eat('{')) return false;
-    unsigned seen = 0;
-    bool first = true;
-    while (!c.eat('}')) {
-        if (!first && !c.eat(',')) return false;
-        first = false;
-        std::string k;
-        if (!c.key(&k) || !c.eat(':')) return false;
-        if (k == "object") { if (!parse_object_tag(c, &o->kind)) return false; seen |= 1; }
-        else if (k == "position") { if (!c.farray(o->position, 3)) return false; seen |= 2; }
-        else if (k == "scale") { if (!c.farray(o->scale, 2)) return false; seen |= 4; }
-        else if (k == "rotation") { if (!c.num(&o->rotation)) return false; seen |= 8; }
-        else return false;
-    }
-    return seen == 15;
+    static const char* const names[] = {"object", "position", "scale", "rotation"};
+    return parse_struct(c, names, 4, [&](int f) {
+        switch (f) {
+            case 0: return parse_world_object(c, &o->kind);
+            case 1: return c.farray(o->position, 3);
+            case 2: return c.farray(o->scale, 2);
+            default: return c.num(&o->rotation);
+        }
+    });
 }
 }  // namespace
 
 int parse_world_json(const char* s, size_t len, prl_world* out) {
     Cur c{s, s + len};
-    unsigned seen = 0;
-    bool first = true;
-    if (!c.eat('{')) goto bad;
-    while (!c.eat('}')) {
-        if (!first && !c.eat(',')) goto bad;
-        first = false;
-        std::string k;
-        if (!c.key(&k) || !c.eat(':')) goto bad;
-        if (k == "player_position") {
-            if (!c.farray(out->player_position, 2)) goto bad;
-            seen |= 1;
-        } else if (k == "objects") {
-            if (!c.eat('[')) goto bad;
-            out->objects.clear();
-            if (!c.eat(']')) {
-                for (;;) {
-                    prl_object o;
-                    memset(&o, 0, sizeof o);
-                    if (!parse_object(c, &o)) goto bad;
-                    out->objects.push_back(o);
-                    if (c.eat(',')) continue;
-                    if (c.eat(']')) break;
-                    goto bad;
-                }
-            }
-            seen |= 2;
-        } else {
-            goto bad;
+    static const char* const names[] = {"player_position", "objects"};
+    bool ok = parse_struct(c, names, 2, [&](int f) {
+        if (f == 0) return c.farray(out->player_position, 2);
+        if (!c.eat('[')) return false;  // Vec<ObjectAndTransform>
+        out->objects.clear();
+        if (c.eat(']')) return true;
+        for (;;) {
+            prl_object o;
+            memset(&o, 0, sizeof o);
+            if (!parse_object(c, &o)) return false;
+            out->objects.push_back(o);
+            if (c.eat(',')) continue;
+            return c.eat(']');
         }
-    }
+    });
     c.ws();
-    if (c.p != c.e || seen != 3) goto bad;
-    return PRL_OK;
-bad:
+    if (ok && c.p == c.e) return PRL_OK;
     set_error("World JSON does not match the serde schema of common.rs:19-49 near byte %ld", (long)(c.p - s));
     return PRL_ERR_PARSE;
 }

@@ -75,17 +75,66 @@ def test_world_create_matches_from_json():
     assert [o.object for o in w.objects] == [0, 1, 0, 0, 0, 0, 2]
 
 
+OBJ = '{"object":"Goal","position":[1,2,3],"scale":[4,5],"rotation":6}'
+
+
 @pytest.mark.parametrize("bad", [
     "", "{", "[]", '{"player_position":[0,0]}', '{"player_position":[0,0,0],"objects":[]}',
     '{"player_position":[0,0],"objects":[{"object":"Gaol","position":[0,0,0],"scale":[1,1],"rotation":0}]}',
     '{"player_position":[0,0],"objects":[{"object":{"Block":{"fixd":true}},"position":[0,0,0],"scale":[1,1],"rotation":0}]}',
     '{"player_position":[0,0],"objects":[{"object":"Goal","position":[0,0],"scale":[1,1],"rotation":0}]}',
-    '{"player_position":[0,0],"objects":[],"extra":1}',
+    # derive(Deserialize): a known field twice is "duplicate field"
+    '{"player_position":[0,0],"objects":[],"objects":[]}',
+    '{"player_position":[0,0],"objects":[{"object":"Goal","object":"Goal","position":[0,0,0],"scale":[1,1],"rotation":0}]}',
+    # serde_json number grammar (RFC 8259): no leading '.', '+' or zeros, no trailing '.', no NaN, f64 overflow
+    '{"player_position":[.5,0],"objects":[]}', '{"player_position":[01,0],"objects":[]}', '{"player_position":[1.,0],"objects":[]}',
+    '{"player_position":[+1,0],"objects":[]}', '{"player_position":[NaN,0],"objects":[]}', '{"player_position":[1e999,0],"objects":[]}',
+    '{"player_position":[-,0],"objects":[]}', '{"player_position":[1e,0],"objects":[]}',
+    # enum forms serde rejects: a struct variant as a bare string, a unit variant with a payload, two tags, no tag
+    '{"player_position":[0,0],"objects":[{"object":"Block","position":[0,0,0],"scale":[1,1],"rotation":0}]}',
+    '{"player_position":[0,0],"objects":[{"object":{"Goal":{}},"position":[0,0,0],"scale":[1,1],"rotation":0}]}',
+    '{"player_position":[0,0],"objects":[{"object":{"Goal":null,"Block":{"fixed":true}},"position":[0,0,0],"scale":[1,1],"rotation":0}]}',
+    '{"player_position":[0,0],"objects":[{"object":{},"position":[0,0,0],"scale":[1,1],"rotation":0}]}',
+    # trailing characters, trailing commas, bad escapes, a lone surrogate, a truncated literal
+    '{"player_position":[0,0],"objects":[]} x', '{"player_position":[0,0],"objects":[],}', '{"player_position":[0,0,],"objects":[]}',
+    r'{"player_position":[0,0],"objects":[],"a":"\x"}', r'{"player_position":[0,0],"objects":[],"a":"\ud800"}',
+    r'{"player_position":[0,0],"objects":[],"a":"\u00"}', '{"player_position":[0,0],"objects":[],"a":tru}',
+    '{"player_position":[0,0],"objects":[],"a":' + "[" * 200 + "]" * 200 + '}',  # recursion limit 128
+    '[[0,0]]', '[[0,0],[],[]]',  # a struct as a sequence needs exactly its fields
+    '{"player_position":[0,0],"objects":[],"a":"line\nbreak"}',  # unescaped control character in a string
+    b'{"player_position":[0,0],"objects":[],"a":"\xff"}',  # not UTF-8 (from_str takes a &str)
 ])
 def test_malformed_json_is_a_parse_error(bad):
     with pytest.raises(prl.PrlError) as e:
         prl.World.from_json(bad)
     assert e.value.status == _lib.PRL_ERR_PARSE
+
+
+@pytest.mark.parametrize("text,n_objects", [
+    # unknown keys are ignored at every level (no deny_unknown_fields on common.rs:19-49), whatever their value
+    ('{"player_position":[0,0],"objects":[],"extra":1}', 0),
+    (r'{"version":{"major":[1,2,{"x":null}],"s":"é😀 \"q\" \n"},"player_position":[0,0],"objects":[%s]}' % OBJ, 1),
+    ('{"player_position":[0,0],"objects":[{"object":"Goal","position":[1,2,3],"colour":"red","scale":[4,5],"rotation":6,"rotation_deg":[]}]}', 1),
+    ('{"player_position":[0,0],"objects":[{"object":{"Block":{"fixed":true,"material":{"friction":0.5}}},"position":[1,2,3],"scale":[4,5],"rotation":6}]}', 1),
+    # unknown keys may repeat
+    ('{"x":1,"x":2,"player_position":[0,0],"objects":[]}', 0),
+    # the unit variant in map form; the struct variant and the structs as sequences (serde visit_seq)
+    ('{"player_position":[0,0],"objects":[{"object":{"Goal":null},"position":[1,2,3],"scale":[4,5],"rotation":6}]}', 1),
+    ('{"player_position":[0,0],"objects":[{"object":{"Block":[false]},"position":[1,2,3],"scale":[4,5],"rotation":6}]}', 1),
+    ('[[0,0],[["Goal",[1,2,3],[4,5],6]]]', 1),
+    # escaped keys compare after unescaping; integers, exponents and -0 are numbers; whitespace anywhere
+    (r'{"play\u0065r_position":[0,0],"objects":[]}', 0),
+    (' {\t"player_position" : [ 1e2 , -0 ] ,\r\n "objects" : [ ] } \n', 0),
+    ('{"player_position":[1E+2,1e-2],"objects":[]}', 0),
+    ('{"player_position":[123456789012345678901234567890,1e300],"objects":[]}', 0),  # f64 -> `as f32` (inf), accepted
+    ('{"player_position":[0,0],"objects":[],"a":' + "[" * 100 + "]" * 100 + '}', 0),
+])
+def test_json_ingest_follows_serde(text, n_objects):
+    w = prl.World.from_json(text)
+    assert len(w.objects) == n_objects
+    if n_objects:
+        o = w.objects[0]
+        assert list(o.position) == [1.0, 2.0, 3.0] and list(o.scale) == [4.0, 5.0] and o.rotation == 6.0
 
 
 def test_capacity_limits_are_reported():
