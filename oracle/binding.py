@@ -19,6 +19,17 @@ class OrcObject(C.Structure):
                 ("rotation", C.c_float), ("kind", C.c_int32)]
 
 
+# Sensitivity variants (prl_oracle.h ORC_VARIANT_*): flip one documented deviation of the oracle
+VARIANT_REVERSE_ORDER, VARIANT_CREATION_ORDER, VARIANT_GJK, VARIANT_WAKE_ON_ZERO_IMPULSE = 1, 2, 4, 8
+VARIANTS = {"D2 descending pair order": 1, "D2 contact-graph edge order": 2, "D1 GJK closest points": 4,
+            "D4 zero impulse wakes": 8, "D1+D2+D4 together": 2 | 4 | 8}
+
+
+def set_default_variant(flags):
+    """Applies to environments created afterwards (rollout_batch included). Tests only."""
+    lib().orc_set_default_variant(int(flags))
+
+
 def build():
     subprocess.check_call(["make", "-C", _HERE, "-s"])
 
@@ -33,6 +44,8 @@ def lib():
         L.orc_env_create.restype = C.c_void_p
         L.orc_env_create.argtypes = [C.POINTER(C.c_float), C.POINTER(OrcObject), C.c_int32]
         L.orc_env_destroy.argtypes = [C.c_void_p]
+        L.orc_set_default_variant.argtypes = [C.c_int32]
+        L.orc_env_set_variant.argtypes = [C.c_void_p, C.c_int32]
         L.orc_env_reset.argtypes = [C.c_void_p]
         L.orc_env_step.argtypes = [C.c_void_p, C.c_uint32]
         L.orc_env_distance_to_goals.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
@@ -71,11 +84,13 @@ def world_to_objects(world):
 class OracleEnv:
     """Single CPU environment with the reference's Environment API."""
 
-    def __init__(self, world):
+    def __init__(self, world, variant=None):
         if isinstance(world, str):
             world = json.loads(world)
         self._pp, self._objs, self._n = world_to_objects(world)
         self._h = lib().orc_env_create(self._pp, self._objs, self._n)
+        if variant is not None:
+            lib().orc_env_set_variant(self._h, int(variant))
 
     def __del__(self):
         if getattr(self, "_h", None):

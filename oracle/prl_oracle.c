@@ -18,6 +18,11 @@
  *      up to pair order).
  *  D4  RigidBody::apply_impulse ignores a zero impulse (does not wake) -- SURVEY A.2 [L].
  *
+ * Each deviation can be flipped at run time (orc_set_default_variant / orc_env_set_variant,
+ * ORC_VARIANT_*) to MEASURE how much the results depend on it (tests/test_oracle_sensitivity.py,
+ * DESIGN.md "Oracle"): GJK closest points (D1), descending / contact-graph edge order (D2),
+ * waking on a zero impulse (D4). The default (0) is the canonical oracle the CUDA path matches.
+ *
  * Everything is f32, evaluated in the crates' expression order, with no FMA contraction
  * (-ffp-contract=off), because rustc never contracts.
  */
@@ -119,7 +124,14 @@ struct orc_env {
     collider_t* colliders0;
     /* derived integration parameters */
     float inv_dt, erp_inv_dt, cfm_factor;
+    /* sensitivity studies only (orc_set_default_variant): which documented deviation to flip */
+    int variant;
+    int* edges;          /* pair indices in contact-graph edge order: appended when a pair is created,
+                            swap-removed when it goes (rapier: InteractionGraph over petgraph) */
+    int nedges;
 };
+static int g_default_variant = 0;
+void orc_set_default_variant(int32_t flags) { g_default_variant = flags; }
 
 /* ------------------------------------------------------------------ small maths */
 static inline v2 V2(float x, float y) { v2 r = {x, y}; return r; }
@@ -453,8 +465,91 @@ static int segment_box_closest(v2 a, v2 b, v2 he, float* u_out, v2* q_out) {
     return 1;
 }
 
+/* Variant ORC_VARIANT_GJK (sensitivity to deviation D1): the same closest points from a textbook
+ * GJK on the Minkowski difference segment - box (parry: query::gjk::closest_points), in the box
+ * frame: simplex of <= 3 support points, start direction `dir0` (parry passes the cached
+ * normal, else the centre offset), termination when the support bound shows the distance is
+ * known to parry's relative tolerance sqrt(10 * f32::EPSILON) or the simplex stops changing.
+ * Returns 0 if the origin is enclosed / reached (the shapes touch), else 1 with the closest
+ * points expressed as (u on the segment, q on the box). */
+typedef struct { v2 w, pa, pb; } cso_pt; /* w = pa - pb, pa on the segment, pb on the box */
+static cso_pt cso_support(v2 a, v2 b, v2 he, v2 dir) {
+    cso_pt r;
+    r.pa = vdot(a, dir) >= vdot(b, dir) ? a : b;
+    v2 nd = vneg(dir);
+    r.pb = V2(copysignf(he.x, nd.x), copysignf(he.y, nd.y)); /* parry: Cuboid::local_support_point */
+    r.w = vsub(r.pa, r.pb);
+    return r;
+}
+static int segment_box_closest_gjk(v2 a, v2 b, v2 he, v2 dir0, float* u_out, v2* q_out) {
+    const float eps_tol = F32_EPS * 10.0f, eps_rel = sqrtf(eps_tol);
+    cso_pt sx[3];
+    int n = 0;
+    float len0 = sqrtf(vdot(dir0, dir0));
+    v2 dir = len0 > eps_tol ? V2(dir0.x / len0, dir0.y / len0) : V2(1.0f, 0.0f);
+    sx[n++] = cso_support(a, b, he, vneg(dir));
+    v2 proj = sx[0].w; /* closest point of the simplex to the origin */
+    float bary[3] = {1.0f, 0.0f, 0.0f};
+    float old_dist = 3.40282347e+38f;
+    for (int iter = 0; iter < 100; ++iter) {
+        float dist = sqrtf(vdot(proj, proj));
+        if (dist <= eps_tol) return 0; /* origin on the simplex: shapes touch */
+        if (!(dist < old_dist)) break;  /* no progress: converged to rounding */
+        old_dist = dist;
+        dir = V2(-proj.x / dist, -proj.y / dist);
+        cso_pt s = cso_support(a, b, he, dir);
+        float min_bound = -vdot(dir, s.w); /* lower bound on the distance */
+        if (min_bound > 0.0f && dist - min_bound <= eps_rel * dist) break; /* parry's exit test */
+        int dup = 0;
+        for (int i = 0; i < n; ++i) if (sx[i].w.x == s.w.x && sx[i].w.y == s.w.y) dup = 1;
+        if (dup) break;
+        sx[n++] = s;
+        /* project the origin on the simplex and reduce it to the supporting face */
+        if (n == 2) {
+            v2 ab = vsub(sx[1].w, sx[0].w);
+            float t = -vdot(sx[0].w, ab) * inv0(vdot(ab, ab));
+            if (t <= 0.0f) { n = 1; bary[0] = 1.0f; proj = sx[0].w; }
+            else if (t >= 1.0f) { sx[0] = sx[1]; n = 1; bary[0] = 1.0f; proj = sx[0].w; }
+            else { bary[0] = 1.0f - t; bary[1] = t; proj = vadd(sx[0].w, vscale(ab, t)); }
+        } else { /* n == 3: triangle */
+            float best = 3.40282347e+38f;
+            int bi = -1, bj = -1;
+            float bt = 0.0f;
+            v2 bp = V2(0.0f, 0.0f);
+            for (int i = 0; i < 3; ++i) {
+                int j = (i + 1) % 3;
+                v2 ab = vsub(sx[j].w, sx[i].w);
+                float t = -vdot(sx[i].w, ab) * inv0(vdot(ab, ab));
+                t = fminf(fmaxf(t, 0.0f), 1.0f);
+                v2 pp = vadd(sx[i].w, vscale(ab, t));
+                float dd = vdot(pp, pp);
+                if (dd < best) { best = dd; bi = i; bj = j; bt = t; bp = pp; }
+            }
+            /* origin inside the triangle? (same sign of the three edge cross products) */
+            float c0 = vcross(vsub(sx[1].w, sx[0].w), vneg(sx[0].w));
+            float c1 = vcross(vsub(sx[2].w, sx[1].w), vneg(sx[1].w));
+            float c2 = vcross(vsub(sx[0].w, sx[2].w), vneg(sx[2].w));
+            if ((c0 >= 0.0f && c1 >= 0.0f && c2 >= 0.0f) || (c0 <= 0.0f && c1 <= 0.0f && c2 <= 0.0f)) return 0;
+            cso_pt pi = sx[bi], pj = sx[bj];
+            if (bt <= 0.0f) { sx[0] = pi; n = 1; bary[0] = 1.0f; }
+            else if (bt >= 1.0f) { sx[0] = pj; n = 1; bary[0] = 1.0f; }
+            else { sx[0] = pi; sx[1] = pj; n = 2; bary[0] = 1.0f - bt; bary[1] = bt; }
+            proj = bp;
+        }
+    }
+    v2 pa = V2(0.0f, 0.0f), pb = V2(0.0f, 0.0f);
+    for (int i = 0; i < n; ++i) { pa = vadd(pa, vscale(sx[i].pa, bary[i])); pb = vadd(pb, vscale(sx[i].pb, bary[i])); }
+    v2 d = vsub(b, a);
+    float u = vdot(vsub(pa, a), d) * inv0(vdot(d, d));
+    *u_out = fminf(fmaxf(u, 0.0f), 1.0f);
+    *q_out = pb;
+    return 1;
+}
+
 /* parry: contact_manifold_pfm_pfm with pfm1 = capsule segment (border radius r), pfm2 = cuboid */
-static void contact_capsule_cuboid(pair_t* m, const iso* pos12, float radius, float hh, v2 he2) {
+static void contact_capsule_cuboid(pair_t* m, const iso* pos12, float radius, float hh, v2 he2, int variant) {
+    v2 cached_n1 = m->n1;
+    int had_normal = (m->n1.x != 0.0f || m->n1.y != 0.0f);
     if (manifold_try_update(m, pos12)) return;
     const float total_prediction = P_PREDICTION + radius + 0.0f;
     v2 sa = V2(0.0f, -hh), sb = V2(0.0f, hh);
@@ -464,7 +559,16 @@ static void contact_capsule_cuboid(pair_t* m, const iso* pos12, float radius, fl
     v2 q;
     v2 p1, p2_1, dir;
     m->npts = 0;
-    if (segment_box_closest(a2, b2, he2, &u, &q)) {
+    int separated;
+    if (variant & ORC_VARIANT_GJK) {
+        /* start direction in the box frame: the cached normal, else towards the box centre */
+        v2 d0 = had_normal ? rot_inv_mul(pos12->c, pos12->s, cached_n1) : vneg(vscale(vadd(a2, b2), 0.5f));
+        separated = segment_box_closest_gjk(a2, b2, he2, d0, &u, &q);
+        if (!separated) separated = segment_box_closest(a2, b2, he2, &u, &q); /* touching: exact routine decides */
+    } else {
+        separated = segment_box_closest(a2, b2, he2, &u, &q);
+    }
+    if (separated) {
         p1 = vadd(sa, vscale(vsub(sb, sa), u));
         p2_1 = iso_mul_pt(pos12, q);
         v2 dp = vsub(p2_1, p1);
@@ -557,13 +661,17 @@ static void detect_collisions(orc_env* e) {
                 m->npts = 0;
                 m->nsolver = 0;
                 m->has_active = 0;
+                if (e->variant & ORC_VARIANT_GJK) m->n1 = V2(0.0f, 0.0f); /* the workspace dies with the pair */
+                for (int i = 0; i < e->nedges; ++i)
+                    if (e->edges[i] == p) { e->edges[i] = e->edges[--e->nedges]; break; } /* swap_remove */
             }
             continue;
         }
+        if (!m->exists) e->edges[e->nedges++] = p;
         m->exists = 1;
         iso pos12 = iso_inv_mul(&co1->pos, &co2->pos);
         if (co1->shape == SHAPE_CAPSULE)
-            contact_capsule_cuboid(m, &pos12, co1->he.x, co1->he.y, co2->he);
+            contact_capsule_cuboid(m, &pos12, co1->he.x, co1->he.y, co2->he, e->variant);
         else
             contact_cuboid_cuboid(m, &pos12, co1->he, co2->he);
         pair_update_solver_contacts(m, co1);
@@ -574,7 +682,9 @@ static void detect_collisions(orc_env* e) {
 /* ------------------------------------------------------------------ bodies */
 
 /* rapier: RigidBody::apply_impulse (deviation D4: zero impulse is a no-op) */
+static int g_wake_on_zero_impulse = 0; /* set from the env's variant at every step (single-threaded studies only) */
 static void body_apply_impulse(body_t* b, v2 j) {
+    if (g_wake_on_zero_impulse && j.x == 0.0f && j.y == 0.0f) { body_wake_strong(b); return; }
     if (j.x != 0.0f || j.y != 0.0f) {
         b->linvel = vadd(b->linvel, vscale(j, b->inv_mass));
         body_wake_strong(b);
@@ -861,7 +971,11 @@ static void pipeline_step(orc_env* e) {
     int* cons_pair = (int*)malloc(sizeof(int) * (size_t)(e->npairs + 1));
     int ncons = 0;
     for (int pass = 0; pass < 2; ++pass) {
-        for (int p = 0; p < e->npairs; ++p) {
+        /* canonical: ascending pair index. Variants (sensitivity to deviation D2): descending,
+         * or the contact graph's edge order (creation order with swap-remove) */
+        const int nwalk = (e->variant & ORC_VARIANT_CREATION_ORDER) ? e->nedges : e->npairs;
+        for (int w = 0; w < nwalk; ++w) {
+            int p = (e->variant & ORC_VARIANT_CREATION_ORDER) ? e->edges[w] : ((e->variant & ORC_VARIANT_REVERSE_ORDER) ? e->npairs - 1 - w : w);
             const pair_t* m = &e->pairs[p];
             if (!m->exists || m->nsolver == 0) continue;
             int h1 = e->colliders[m->c1].body, h2 = e->colliders[m->c2].body;
@@ -1066,6 +1180,8 @@ orc_env* orc_env_create(const float player_position[2], const orc_object* objs, 
         np = k;
     }
     e->npairs = np;
+    e->edges = (int*)calloc((size_t)(np ? np : 1), sizeof(int));
+    e->variant = g_default_variant;
     memcpy(e->bodies0, e->bodies, sizeof(body_t) * (size_t)e->nbodies);
     memcpy(e->colliders0, e->colliders, sizeof(collider_t) * (size_t)e->ncolliders);
     orc_env_reset(e);
@@ -1081,6 +1197,7 @@ void orc_env_reset(orc_env* e) {
         e->pairs[p].c1 = c1;
         e->pairs[p].c2 = c2;
     }
+    e->nedges = 0;
     e->won = 0;
     e->fresh = 1;
 }
@@ -1088,7 +1205,7 @@ void orc_env_reset(orc_env* e) {
 void orc_env_destroy(orc_env* e) {
     if (!e) return;
     free(e->bodies); free(e->bodies0); free(e->colliders); free(e->colliders0);
-    free(e->pairs); free(e->goals); free(e);
+    free(e->pairs); free(e->goals); free(e->edges); free(e);
 }
 
 /* ref: common.rs:175-195 */
@@ -1109,6 +1226,7 @@ int orc_env_distance_to_goals(const orc_env* e, float* out) {
 }
 
 int orc_env_won(const orc_env* e) { return e->won; }
+void orc_env_set_variant(orc_env* e, int32_t flags) { e->variant = flags; }
 
 /* ref: common.rs:215-340 */
 void orc_env_step(orc_env* e, uint32_t mv) {
@@ -1118,8 +1236,13 @@ void orc_env_step(orc_env* e, uint32_t mv) {
     int cap = 2 * e->npairs + 2, nfc = 0;
     v2* fpt = (v2*)malloc(sizeof(v2) * (size_t)cap);
     int* fbody = (int*)malloc(sizeof(int) * (size_t)cap);
+    g_wake_on_zero_impulse = (e->variant & ORC_VARIANT_WAKE_ON_ZERO_IMPULSE) != 0;
     if (!e->fresh) {
-        for (int p = 0; p < e->npairs; ++p) {
+        /* contacts_with(player_collider): canonical ascending pair order; variants: descending, or
+         * the player's adjacency list in the contact graph (petgraph: newest edge first) */
+        const int nwalk = (e->variant & ORC_VARIANT_CREATION_ORDER) ? e->nedges : e->npairs;
+        for (int w = 0; w < nwalk; ++w) {
+            int p = (e->variant & ORC_VARIANT_CREATION_ORDER) ? e->edges[e->nedges - 1 - w] : ((e->variant & ORC_VARIANT_REVERSE_ORDER) ? e->npairs - 1 - w : w);
             const pair_t* m = &e->pairs[p];
             if (m->c1 != 0 || !m->exists) continue; /* contacts_with(player_collider) */
             if (!m->has_active) continue;

@@ -40,6 +40,18 @@ typedef struct {
 
 typedef struct orc_env orc_env;
 
+/* Sensitivity studies (tests/test_oracle_sensitivity.py): flip one of the oracle's documented
+ * deviations from the crates. 0 = the canonical oracle. The default applies to environments created
+ * afterwards (orc_rollout_batch included); not thread safe, tests only. */
+enum {
+    ORC_VARIANT_REVERSE_ORDER = 1,        /* D2: Gauss-Seidel / floor-contact scan in descending pair order */
+    ORC_VARIANT_CREATION_ORDER = 2,       /* D2: contact-graph edge order (pair creation order, swap-remove on removal) */
+    ORC_VARIANT_GJK = 4,                  /* D1: capsule-cuboid closest points by GJK with parry's tolerance */
+    ORC_VARIANT_WAKE_ON_ZERO_IMPULSE = 8  /* D4: apply_impulse(0, wake_up = true) wakes the body */
+};
+void orc_set_default_variant(int32_t flags);
+void orc_env_set_variant(orc_env*, int32_t flags);
+
 /* Environment::from_world (common.rs:162-172). Returns NULL on allocation failure. */
 orc_env* orc_env_create(const float player_position[2], const orc_object* objs, int32_t n);
 void orc_env_destroy(orc_env*);

@@ -7,6 +7,7 @@
 // must be compiled without FMA contraction (-ffp-contract=off).
 #include <math.h>
 #include <stdarg.h>
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -16,6 +17,11 @@
 
 #include "prl_host.h"
 #include "prl_libm.h"
+
+// layout of the PODs of include/prl.h as the Rust (rust/src/ffi.rs) and ctypes (_lib.py) mirrors declare them
+static_assert(sizeof(prl_object) == 28 && offsetof(prl_object, scale) == 12 && offsetof(prl_object, rotation) == 20 && offsetof(prl_object, kind) == 24, "prl_object layout");
+static_assert(sizeof(prl_ga_config) == 40 && offsetof(prl_ga_config, number_of_agents) == 8 && offsetof(prl_ga_config, repeat_move) == 16 &&
+              offsetof(prl_ga_config, mutation_rate) == 20 && offsetof(prl_ga_config, keep_best) == 24 && offsetof(prl_ga_config, seed) == 32, "prl_ga_config layout");
 
 namespace prl {
 

@@ -1,4 +1,4 @@
-//! `extern "C"` bindings of include/prl.h (ABI version 1). One declaration per exported symbol;
+//! `extern "C"` bindings of include/prl.h (ABI version 2). One declaration per exported symbol;
 //! tests/test_abi.py checks that libprl.so exports every symbol named here.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
@@ -27,6 +27,33 @@ pub struct prl_ga_config {
     pub mutation_rate: f32,
     pub keep_best: i32,
     pub seed: u64,
+}
+
+// Layout of the two PODs that cross the ABI by value/pointer: sizes and field offsets of the C
+// structs in include/prl.h (static_asserted there too, csrc/prl_world.cc; tests/test_abi.py
+// compares these numbers with the ctypes mirror).
+pub const PRL_ABI_VERSION: i32 = 2;
+pub const PRL_OBJECT_SIZE: usize = 28;
+pub const PRL_GA_CONFIG_SIZE: usize = 40;
+const _: () = {
+    use std::mem::{align_of, size_of};
+    assert!(size_of::<prl_object>() == PRL_OBJECT_SIZE && align_of::<prl_object>() == 4);
+    assert!(size_of::<prl_ga_config>() == PRL_GA_CONFIG_SIZE && align_of::<prl_ga_config>() == 8);
+};
+#[cfg(test)]
+mod layout {
+    use super::*;
+    use std::mem::offset_of;
+    #[test]
+    fn field_offsets_match_include_prl_h() {
+        assert_eq!((offset_of!(prl_object, position), offset_of!(prl_object, scale), offset_of!(prl_object, rotation), offset_of!(prl_object, kind)), (0, 12, 20, 24));
+        assert_eq!(
+            (offset_of!(prl_ga_config, number_of_steps), offset_of!(prl_ga_config, number_of_agents), offset_of!(prl_ga_config, repeat_move),
+             offset_of!(prl_ga_config, mutation_rate), offset_of!(prl_ga_config, keep_best), offset_of!(prl_ga_config, seed)),
+            (0, 8, 16, 20, 24, 32)
+        );
+        assert_eq!(unsafe { prl_abi_version() }, PRL_ABI_VERSION);
+    }
 }
 
 pub enum prl_world {}

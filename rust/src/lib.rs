@@ -180,10 +180,9 @@ impl Drop for BatchedEnvironment {
 }
 
 /// The reference's `GeneticAlgorithm` (main.rs:18-38) with the population evaluated and bred on
-/// the GPU. `train` has the signature of `Algorithm::train` (algorithm.rs:27) up to the agent type:
-/// inside the reference crate, map `(f32, Vec<Move>)` to `(f32, GeneticAgent { moves, curr: 0,
-/// repeat_move })` (main.rs:112-120) -- see INTEGRATION.md.
-#[derive(PartialEq, Clone, Copy)]
+/// the GPU(s). `train` has the body of `Algorithm::train` (algorithm.rs:27) up to the agent type:
+/// `examples/batched_main.rs` wraps it into the reference's three traits.
+#[derive(PartialEq, Clone)]
 pub struct BatchedGeneticAlgorithm {
     pub number_of_steps: usize,
     pub number_of_agents: usize,
@@ -191,16 +190,34 @@ pub struct BatchedGeneticAlgorithm {
     pub mutation_rate: f32,
     pub keep_best: bool,
     pub seed: u64,
-    pub device: i32,
+    /// CUDA devices to spread the population over (one slice per entry; peer access between
+    /// them is required when there are several -- `prl_ga_create_multi`)
+    pub devices: Vec<i32>,
 }
 
 impl Default for BatchedGeneticAlgorithm {
     fn default() -> Self {
-        BatchedGeneticAlgorithm { number_of_steps: 1000, number_of_agents: 1000, repeat_move: 20, mutation_rate: 0.1, keep_best: false, seed: 0xB200, device: 0 }
+        BatchedGeneticAlgorithm { number_of_steps: 1000, number_of_agents: 1000, repeat_move: 20, mutation_rate: 0.1, keep_best: false, seed: 0xB200,
+                                  devices: vec![0] }
     }
 }
 
+/// number of CUDA devices the library can see (0: no GPU -- every compute call fails, there is no CPU path)
+pub fn device_count() -> i32 {
+    unsafe { ffi::prl_device_count() }
+}
+
 impl BatchedGeneticAlgorithm {
+    /// all visible devices
+    pub fn on_all_devices(mut self) -> Self {
+        self.devices = (0..device_count().max(1)).collect();
+        self
+    }
+
+    /// main.rs:41-163: sends `(best score, best genome)` once per generation until the receiver is
+    /// dropped (main.rs:121-124). One `prl_ga_step_generation` call is one iteration of the
+    /// reference's `loop` (main.rs:86-162); with several devices the library exchanges the
+    /// generation over peer memory itself.
     pub fn train(&self, world: World, sender: crossbeam::channel::Sender<(f32, Vec<Move>)>) -> Result<(), PrlError> {
         let wh = WorldHandle::new(&world)?;
         let cfg = ffi::prl_ga_config {
@@ -212,7 +229,7 @@ impl BatchedGeneticAlgorithm {
             seed: self.seed,
         };
         let mut ga = ptr::null_mut();
-        check(unsafe { ffi::prl_ga_create(wh.0, &cfg, self.device, ptr::null_mut(), 0, 1, &mut ga) })?;
+        check(unsafe { ffi::prl_ga_create_multi(wh.0, &cfg, self.devices.as_ptr(), self.devices.len() as i32, &mut ga) })?;
         struct Guard(*mut ffi::prl_ga);
         impl Drop for Guard {
             fn drop(&mut self) {
@@ -220,17 +237,15 @@ impl BatchedGeneticAlgorithm {
             }
         }
         let _guard = Guard(ga);
-        check(unsafe { ffi::prl_ga_init(ga) })?;
         let genome_len = self.number_of_steps / self.repeat_move;
         loop {
             let mut score = 0f32;
             let mut genome = vec![0u8; genome_len];
-            check(unsafe { ffi::prl_ga_best(ga, &mut score, genome.as_mut_ptr(), ptr::null_mut()) })?;
+            check(unsafe { ffi::prl_ga_step_generation(ga, &mut score, genome.as_mut_ptr(), ptr::null_mut()) })?;
             let moves = genome.iter().map(|b| Move { left: b & 1 != 0, right: b & 2 != 0, up: b & 4 != 0 }).collect();
             if sender.send((score, moves)).is_err() {
                 return Ok(()); // receiver dropped: stop training (main.rs:121-124)
             }
-            check(unsafe { ffi::prl_ga_next_generation(ga) })?;
         }
     }
 }

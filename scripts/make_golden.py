@@ -4,8 +4,10 @@
 The reference (Rust + rapier2d 0.17.2 from crates.io) cannot be built or run in this image and
 ships no golden vectors, so these fixtures are produced by the CPU ORACLE
 (oracle/prl_oracle.c) -- they pin the oracle and the CUDA path against regressions and against
-each other, not against rapier itself: PARITY UNPINNED. If real-rapier dumps ever become
-available, drop them in tests/golden/ in the same format (see tests/test_golden.py).
+each other, not against rapier itself: PARITY UNPINNED. They are REGRESSION PINS (`source =
+"oracle"`). Fixtures from the real crate are produced by rust/examples/dump_golden.rs +
+scripts/import_rapier_golden.py (`source = "rapier"`, `--request` below writes their case list)
+and are compared in tolerance mode by tests/test_golden.py.
 
 Format, per world: genomes (16 x 50 uint8), repeat_move, number_of_steps, score (f32), step_of_win
 (i32), steps_run (i32) with the reference's early exit, and the full body trajectory of the first
@@ -26,6 +28,13 @@ from conftest import edge_case_worlds, many_supports_world  # noqa: E402
 
 def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
+    if "--request" in sys.argv:
+        # the cases rust/examples/dump_golden.rs runs on the REAL reference (see scripts/import_rapier_golden.py)
+        sys.path.insert(0, os.path.join(ROOT, "scripts"))
+        from import_rapier_golden import request_cases
+        json.dump({"cases": request_cases()}, open(os.path.join(out_dir, "request.json"), "w"))
+        print("wrote", os.path.join(out_dir, "request.json"))
+        return
     worlds = {name: json.load(open(os.path.join(ROOT, "worlds", f"{name}.json"))) for name in ("right", "jump", "push")}
     # levels the editor can produce that the shipped examples do not cover; their JSON travels in the fixture
     worlds.update({f"edge_{k}": v for k, v in edge_case_worlds().items()})
@@ -45,7 +54,7 @@ def main():
             for t in range(steps):
                 env.step(int(genomes[g][t // repeat]))
                 traj[gi, t] = env.state()
-        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), world_json=np.array(json.dumps(world)), genomes=genomes, repeat_move=repeat,
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), source=np.array("oracle"), world_json=np.array(json.dumps(world)), genomes=genomes, repeat_move=repeat,
                             number_of_steps=steps, score=score, step_of_win=win, steps_run=run,
                             traj_genomes=np.array((2, 6, 8, 9)), traj=traj[:, ::10].copy())
         print(name, "scores", score[:8], "wins", win)

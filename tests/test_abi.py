@@ -36,6 +36,20 @@ def test_rust_facade_binds_exactly_the_exported_symbols():
     assert rust == declared_symbols()
 
 
+def test_pod_layouts_agree_between_c_rust_and_ctypes():
+    """prl_object / prl_ga_config cross the ABI by pointer: the C header (static_assert in
+    csrc/prl_world.cc), rust/src/ffi.rs (const assertions) and the ctypes mirror must agree."""
+    text = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    rust = {k: int(v) for k, v in re.findall(r"pub const (PRL_[A-Z_]+): \w+ = (\d+);", text)}
+    assert rust["PRL_OBJECT_SIZE"] == C.sizeof(_lib.PrlObject) == 28
+    assert rust["PRL_GA_CONFIG_SIZE"] == C.sizeof(_lib.PrlGaConfig) == 40
+    assert rust["PRL_ABI_VERSION"] == _lib.lib().prl_abi_version()
+    assert [getattr(_lib.PrlObject, f).offset for f, _ in _lib.PrlObject._fields_] == [0, 12, 20, 24]
+    assert [getattr(_lib.PrlGaConfig, f).offset for f, _ in _lib.PrlGaConfig._fields_] == [0, 8, 16, 20, 24, 32]
+    cc = open(os.path.join(ROOT, "physics_reinforcement_learning_environment_b200", "csrc", "prl_world.cc")).read()
+    assert "static_assert(sizeof(prl_object) == 28" in cc and "static_assert(sizeof(prl_ga_config) == 40" in cc
+
+
 def test_product_does_not_link_or_import_the_oracle():
     # the oracle is test infrastructure: no product source may mention it
     pkg = os.path.join(ROOT, "physics_reinforcement_learning_environment_b200")
