@@ -129,6 +129,26 @@ int prl_batch_rollout(prl_batch*, const uint8_t* genomes, int32_t genome_len, in
  * (the GA's score, main.rs:50), 1-based step at which won() first became true (-1: never) and
  * the number of steps taken. Host or device buffers; any may be NULL. Synchronises. */
 int prl_batch_rollout_info(prl_batch*, float* out_score, int32_t* out_step_of_win, int32_t* out_steps);
+/* ---- Observation-driven agents: Agent::get_move(&mut self, &Environment) (algorithm.rs:8-11) in batch.
+ * Observation of one environment, D = prl_batch_observation_dim = 9 * n_bodies + 4 floats: per body
+ * (from_world handle order) x, y, cos, sin, vx, vy, angvel, sleep_timer, sleeping (what
+ * rigid_body_set() exposes, common.rs:201-211), then the ground-contact scan Environment::step makes
+ * from narrow_phase / collider_set() (common.rs:223-244): on_ground (0/1), number of floor contacts,
+ * 1 if the player has an active contact with a pushable block; then distance_to_goals() in pixels
+ * (+inf without goals). Contacts are those of the end of the previous step (none before the first). */
+int32_t prl_batch_observation_dim(const prl_batch*);
+/* out: n_envs x D floats, host or device */
+int prl_batch_get_observation(prl_batch*, float* out);
+/* A per-agent two-layer perceptron evaluated INSIDE the fused rollout, every step, in place of the
+ * genome look-up of prl_batch_rollout: h = max(W1 obs + b1, 0) (hidden <= 32 units), out = W2 h + b2,
+ * Move = (out[0] > 0, out[1] > 0, out[2] > 0) = (left, right, up). params: P x n_envs floats,
+ * parameter-major (params[p * n_envs + env]), P = prl_policy_num_params = hidden * (D + 1) +
+ * 3 * (hidden + 1): W1 row j at p = j * (D + 1) + i with its bias at i = D, then W2 row k at
+ * hidden * (D + 1) + k * (hidden + 1) + j with its bias at j = hidden. From the from_world state;
+ * scores / win steps as prl_batch_rollout (main.rs:44-70 with repeat_move = 1). Host or device buffers. */
+int32_t prl_policy_num_params(const prl_batch*, int32_t hidden);
+int prl_batch_rollout_policy(prl_batch*, const float* params, int32_t hidden, int32_t number_of_steps,
+                             int32_t early_exit, float* out_score, int32_t* out_step_of_win);
 /* Replay for the viewers (train.rs:132-159: `update_visualization` steps a fresh Environment with
  * `agent.get_move()` once per frame and copies every body's transform to its sprite): n fresh
  * from_world environments play one GeneticAgent each (main.rs:276-284: genes repeated

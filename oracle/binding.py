@@ -63,6 +63,13 @@ def lib():
         L.orc_rollout_batch.argtypes = [C.POINTER(C.c_float), C.POINTER(OrcObject), C.c_int32, C.c_void_p,
                                         C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                         C.c_void_p, C.c_void_p]
+        L.orc_env_observation_dim.argtypes = [C.c_void_p]
+        L.orc_env_observation.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_policy_move.restype = C.c_uint32
+        L.orc_policy_move.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
+        L.orc_rollout_policy_batch.restype = C.c_int64
+        L.orc_rollout_policy_batch.argtypes = [C.POINTER(C.c_float), C.POINTER(OrcObject), C.c_int32, C.c_void_p, C.c_int64, C.c_int32,
+                                               C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -128,6 +135,12 @@ class OracleEnv:
     def state(self):
         return np.stack([self.body_state(b) for b in range(self.num_bodies)])
 
+    def observation(self):
+        """What Agent::get_move can read between two steps (layout of prl_batch_get_observation)."""
+        out = np.zeros(lib().orc_env_observation_dim(self._h), dtype=np.float32)
+        lib().orc_env_observation(self._h, out.ctypes.data)
+        return out
+
     @property
     def num_pairs(self):
         return lib().orc_env_num_pairs(self._h)
@@ -161,4 +174,18 @@ def rollout_batch(world, genomes, repeat_move, number_of_steps, early_exit=True,
     win = np.empty(n_envs, dtype=np.int32)
     steps = lib().orc_rollout_batch(pp, objs, n, g.ctypes.data, n_envs, glen, repeat_move, number_of_steps,
                                     1 if early_exit else 0, n_threads, score.ctypes.data, win.ctypes.data)
+    return score, win, int(steps)
+
+
+def rollout_policy_batch(world, params, hidden, number_of_steps, early_exit=True, n_threads=1):
+    """params: (P, n_envs) float32, parameter-major (include/prl.h prl_batch_rollout_policy)."""
+    if isinstance(world, str):
+        world = json.loads(world)
+    pp, objs, n = world_to_objects(world)
+    th = np.ascontiguousarray(params, dtype=np.float32)
+    n_envs = th.shape[1]
+    score = np.empty(n_envs, dtype=np.float32)
+    win = np.empty(n_envs, dtype=np.int32)
+    steps = lib().orc_rollout_policy_batch(pp, objs, n, th.ctypes.data, n_envs, int(hidden), number_of_steps,
+                                           1 if early_exit else 0, n_threads, score.ctypes.data, win.ctypes.data)
     return score, win, int(steps)

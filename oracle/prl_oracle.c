@@ -1413,3 +1413,127 @@ int64_t orc_rollout_batch(const float player_position[2], const orc_object* objs
     free(jobs);
     return total;
 }
+
+/* ------------------------------------------------------------------ observation-driven agents
+ * The batched form of Agent::get_move(&mut self, &Environment) (ref: algorithm.rs:8-11) that the
+ * product evaluates inside its fused rollout (include/prl.h prl_batch_rollout_policy): the
+ * observation an agent can read between two steps and a two-layer perceptron on it. Restated
+ * here independently so the kernels can be checked bit for bit. */
+int32_t orc_env_observation_dim(const orc_env* e) { return 9 * e->nbodies + 4; }
+
+/* obs: per body x, y, cos, sin, vx, vy, angvel, sleep timer, sleeping (ref: common.rs:201-211);
+ * on_ground, number of floor contacts, touching a pushable block (the scan of ref:
+ * common.rs:223-244 over narrow_phase.contacts_with(player_collider)); distance_to_goals in px */
+void orc_env_observation(const orc_env* e, float* obs) {
+    for (int b = 0; b < e->nbodies; ++b) orc_env_body_state(e, b, obs + 9 * b);
+    const body_t* player = &e->bodies[0];
+    float lower_y = player->pos.t.y - PLAYER_DEPTH * BEVY_TO_PHYSICS_SCALE / 2.0f;
+    int nfc = 0, touching = 0;
+    if (!e->fresh) {
+        for (int p = 0; p < e->npairs; ++p) {
+            const pair_t* m = &e->pairs[p];
+            if (m->c1 != 0 || !m->exists || !m->has_active) continue;
+            if (e->colliders[m->c2].body >= 0) touching = 1;
+            for (int k = 0; k < m->nsolver; ++k) {
+                float r = PLAYER_RADIUS * BEVY_TO_PHYSICS_SCALE;
+                float qy = (m->sc[k].point.y - lower_y) / r;
+                if (qy < -0.707f) ++nfc;
+            }
+        }
+    }
+    float* x = obs + 9 * e->nbodies;
+    x[0] = nfc > 0 ? 1.0f : 0.0f;
+    x[1] = (float)nfc;
+    x[2] = touching ? 1.0f : 0.0f;
+    float d = INFINITY;
+    orc_env_distance_to_goals(e, &d);
+    x[3] = d;
+}
+
+/* h = max(W1 obs + b1, 0), out = W2 h + b2, Move bit k = out_k > 0; sums left to right in f32.
+ * theta[p * stride]: parameter p of this agent (parameter-major storage, stride = agents) */
+uint32_t orc_policy_move(const float* theta, int64_t stride, int32_t hidden, int32_t D, const float* obs) {
+    float h[64];
+    for (int j = 0; j < hidden; ++j) {
+        const float* row = theta + (int64_t)j * (D + 1) * stride;
+        float acc = row[(int64_t)D * stride];
+        for (int i = 0; i < D; ++i) acc = acc + row[(int64_t)i * stride] * obs[i];
+        h[j] = fmaxf(acc, 0.0f);
+    }
+    uint32_t mv = 0;
+    const float* w2 = theta + (int64_t)hidden * (D + 1) * stride;
+    for (int k = 0; k < 3; ++k) {
+        const float* row = w2 + (int64_t)k * (hidden + 1) * stride;
+        float acc = row[(int64_t)hidden * stride];
+        for (int j = 0; j < hidden; ++j) acc = acc + row[(int64_t)j * stride] * h[j];
+        if (acc > 0.0f) mv |= 1u << k;
+    }
+    return mv;
+}
+
+/* ref: main.rs:44-70 with the agent's get_move in place of the genome, repeat_move = 1 */
+float orc_rollout_policy(orc_env* e, const float* theta, int64_t stride, int32_t hidden, int32_t number_of_steps,
+                         int32_t early_exit, int32_t* step_of_win, int32_t* steps_run) {
+    orc_env_reset(e);
+    float score = INFINITY;
+    int32_t steps = 0, win_step = -1;
+    const int32_t D = orc_env_observation_dim(e);
+    float* obs = (float*)malloc(sizeof(float) * (size_t)D);
+    for (int32_t t = 0; t < number_of_steps; ++t) {
+        orc_env_observation(e, obs);
+        orc_env_step(e, orc_policy_move(theta, stride, hidden, D, obs));
+        ++steps;
+        float d = 0.0f;
+        orc_env_distance_to_goals(e, &d);
+        score = fminf(score, d);
+        if (e->won && win_step < 0) win_step = steps;
+        if (e->won && early_exit) break;
+    }
+    free(obs);
+    if (step_of_win) *step_of_win = win_step;
+    if (steps_run) *steps_run = steps;
+    return score;
+}
+
+typedef struct {
+    const float* player; const orc_object* objs; int32_t n;
+    const float* theta; int64_t n_envs, lo, hi; int32_t hidden, number_of_steps, early_exit;
+    float* out_score; int32_t* out_win; int64_t steps;
+} policy_job_t;
+
+static void* policy_worker(void* arg) {
+    policy_job_t* j = (policy_job_t*)arg;
+    orc_env* e = orc_env_create(j->player, j->objs, j->n);
+    j->steps = 0;
+    for (int64_t i = j->lo; i < j->hi; ++i) {
+        int32_t win, run;
+        float s = orc_rollout_policy(e, j->theta + i, j->n_envs, j->hidden, j->number_of_steps, j->early_exit, &win, &run);
+        if (j->out_score) j->out_score[i] = s;
+        if (j->out_win) j->out_win[i] = win;
+        j->steps += run;
+    }
+    orc_env_destroy(e);
+    return NULL;
+}
+
+int64_t orc_rollout_policy_batch(const float player_position[2], const orc_object* objs, int32_t n, const float* theta,
+                                 int64_t n_envs, int32_t hidden, int32_t number_of_steps, int32_t early_exit,
+                                 int32_t n_threads, float* out_score, int32_t* out_step_of_win) {
+    if (n_threads < 1) n_threads = 1;
+    if ((int64_t)n_threads > n_envs) n_threads = (int32_t)(n_envs > 0 ? n_envs : 1);
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    policy_job_t* jobs = (policy_job_t*)calloc((size_t)n_threads, sizeof(policy_job_t));
+    for (int t = 0; t < n_threads; ++t) {
+        policy_job_t* j = &jobs[t];
+        j->player = player_position; j->objs = objs; j->n = n; j->theta = theta; j->n_envs = n_envs;
+        j->lo = n_envs * t / n_threads; j->hi = n_envs * (t + 1) / n_threads;
+        j->hidden = hidden; j->number_of_steps = number_of_steps; j->early_exit = early_exit;
+        j->out_score = out_score; j->out_win = out_step_of_win;
+        pthread_create(&th[t], NULL, policy_worker, j);
+    }
+    int64_t total = 0;
+    for (int t = 0; t < n_threads; ++t) { pthread_join(th[t], NULL); total += jobs[t].steps; }
+    free(th);
+    free(jobs);
+    return total;
+}

@@ -94,6 +94,20 @@ int64_t orc_rollout_batch(const float player_position[2], const orc_object* objs
                           int32_t repeat_move, int32_t number_of_steps, int32_t early_exit,
                           int32_t n_threads, float* out_score, int32_t* out_step_of_win);
 
+/* Observation-driven agents (ref: algorithm.rs:8-11 Agent::get_move(&mut self, &Environment)):
+ * observation = 9 floats per body (orc_env_body_state) + on_ground, floor-contact count, touching a
+ * pushable block (the scan of common.rs:223-244) + distance_to_goals (px); policy = two-layer
+ * perceptron, parameter p of an agent at theta[p * stride] (layout of include/prl.h
+ * prl_batch_rollout_policy). */
+int32_t orc_env_observation_dim(const orc_env*);
+void orc_env_observation(const orc_env*, float* obs);
+uint32_t orc_policy_move(const float* theta, int64_t stride, int32_t hidden, int32_t obs_dim, const float* obs);
+float orc_rollout_policy(orc_env*, const float* theta, int64_t stride, int32_t hidden, int32_t number_of_steps,
+                         int32_t early_exit, int32_t* step_of_win, int32_t* steps_run);
+int64_t orc_rollout_policy_batch(const float player_position[2], const orc_object* objs, int32_t n, const float* theta,
+                                 int64_t n_envs, int32_t hidden, int32_t number_of_steps, int32_t early_exit,
+                                 int32_t n_threads, float* out_score, int32_t* out_step_of_win);
+
 #ifdef __cplusplus
 }
 #endif

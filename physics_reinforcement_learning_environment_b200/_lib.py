@@ -69,6 +69,10 @@ _SIGNATURES = {
                                     C.c_void_p, C.c_void_p]),
     "prl_batch_rollout_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "prl_batch_trajectory": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "prl_batch_observation_dim": (C.c_int32, [C.c_void_p]),
+    "prl_batch_get_observation": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "prl_policy_num_params": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "prl_batch_rollout_policy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "prl_batch_sync": (C.c_int, [C.c_void_p]),
     "prl_batch_launch_count": (C.c_int64, [C.c_void_p]),
     "prl_ga_create": (C.c_int, [C.c_void_p, C.POINTER(PrlGaConfig), C.c_int32, C.c_void_p, C.c_int32, C.c_int32,

@@ -111,6 +111,39 @@ class BatchedEnvironment:
             _ptr(out_step_of_win, np.int32, self.n_envs, "out_step_of_win")))
         return out_score, out_step_of_win
 
+    @property
+    def observation_dim(self) -> int:
+        return _lib.lib().prl_batch_observation_dim(self._h)
+
+    def observation(self, out=None):
+        """What `Agent::get_move(&mut self, &Environment)` (algorithm.rs:9) can read between two
+        steps, (n_envs, D = 9 n_bodies + 4) float32: per body x, y, cos, sin, vx, vy, angvel, sleep
+        timer, sleeping; on_ground, number of floor contacts, touching a pushable block (the scan of
+        common.rs:223-244); distance_to_goals in pixels. `out` may be a torch CUDA tensor."""
+        D = self.observation_dim
+        if out is None:
+            out = np.empty((self.n_envs, D), dtype=np.float32)
+        _lib.check(_lib.lib().prl_batch_get_observation(self._h, _ptr(out, np.float32, self.n_envs * D, "out")))
+        return out
+
+    def policy_num_params(self, hidden: int) -> int:
+        return _lib.lib().prl_policy_num_params(self._h, int(hidden))
+
+    def rollout_policy(self, params, hidden: int, number_of_steps: int, early_exit: bool = True,
+                       out_score=None, out_step_of_win=None) -> Tuple[np.ndarray, np.ndarray]:
+        """The fitness rollout of main.rs:44-70 with a per-agent two-layer perceptron evaluated inside
+        the kernel every step in place of the genome (include/prl.h prl_batch_rollout_policy).
+        params: (policy_num_params(hidden), n_envs) float32, parameter-major; numpy or torch CUDA."""
+        P = self.policy_num_params(hidden)
+        if out_score is None:
+            out_score = np.empty(self.n_envs, dtype=np.float32)
+        if out_step_of_win is None:
+            out_step_of_win = np.empty(self.n_envs, dtype=np.int32)
+        _lib.check(_lib.lib().prl_batch_rollout_policy(
+            self._h, _ptr(params, np.float32, P * self.n_envs, "params"), int(hidden), int(number_of_steps), 1 if early_exit else 0,
+            _ptr(out_score, np.float32, self.n_envs, "out_score"), _ptr(out_step_of_win, np.int32, self.n_envs, "out_step_of_win")))
+        return out_score, out_step_of_win
+
     def trajectory(self, genomes, repeat_move: int, number_of_steps: int):
         """Replay for the viewers (train.rs:132-159): every genome (a GeneticAgent, main.rs:276-284)
         is played on a fresh from_world environment for `number_of_steps` steps in one launch.

@@ -368,6 +368,60 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
     return PRL_OK;
 }
 
+int32_t prl_batch_observation_dim(const prl_batch* b) { return b ? policy_obs_dim(b->host_world.n_bodies) : 0; }
+int32_t prl_policy_num_params(const prl_batch* b, int32_t hidden) {
+    if (!b || hidden < 1 || hidden > kMaxHidden) return -1;
+    return policy_num_params(b->host_world.n_bodies, hidden);
+}
+
+int prl_batch_get_observation(prl_batch* b, float* out) {
+    if (!b || !out) { set_error("prl_batch_get_observation: null argument"); return PRL_ERR_INVALID; }
+    DeviceGuard g(b->device);
+    const size_t bytes = (size_t)b->n * policy_obs_dim(b->host_world.n_bodies) * 4;
+    const bool dev = is_device_ptr(out);
+    float* d = out;
+    if (!dev) {
+        int rc = ensure_stage(&b->stage2, &b->stage2_bytes, bytes);
+        if (rc != PRL_OK) return rc;
+        d = (float*)b->stage2;
+    }
+    PRL_DISPATCH(pick_variant(b->host_world), observation_kernel, grid_for(b->n), b->stream, b->dev_world, b->state, b->n, d);
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (!dev) {
+        CUDA_TRY(cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, b->stream));
+        CUDA_TRY(cudaStreamSynchronize(b->stream));
+    }
+    return PRL_OK;
+}
+
+int prl_batch_rollout_policy(prl_batch* b, const float* params, int32_t hidden, int32_t number_of_steps, int32_t early_exit,
+                             float* out_score, int32_t* out_step_of_win) {
+    if (!b || !params || hidden < 1 || hidden > kMaxHidden || number_of_steps < 0) {
+        set_error("prl_batch_rollout_policy: bad argument (1 <= hidden <= %d)", kMaxHidden);
+        return PRL_ERR_INVALID;
+    }
+    if (b->host_world.n_goals == 0) { set_error("the world has no goal: the rollout's distance_to_goals().unwrap() would panic (main.rs:50)"); return PRL_ERR_NO_GOAL; }
+    DeviceGuard g(b->device);
+    const size_t pbytes = (size_t)policy_num_params(b->host_world.n_bodies, hidden) * (size_t)b->n * 4;
+    const float* dp = params;
+    if (!is_device_ptr(params)) {
+        int rc = ensure_stage(&b->stage, &b->stage_bytes, pbytes);
+        if (rc != PRL_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(b->stage, params, pbytes, cudaMemcpyHostToDevice, b->stream));
+        dp = (const float*)b->stage;
+    }
+    const bool score_host = out_score && !is_device_ptr(out_score), win_host = out_step_of_win && !is_device_ptr(out_step_of_win);
+    PRL_DISPATCH(pick_variant(b->host_world), policy_rollout_kernel, grid_for(b->n), b->stream, b->dev_world, b->state, b->n, dp, hidden,
+                 number_of_steps, early_exit, score_host ? nullptr : out_score, win_host ? nullptr : out_step_of_win, b->overflow);
+    ++b->launches;
+    CUDA_TRY(cudaGetLastError());
+    if (score_host) CUDA_TRY(cudaMemcpyAsync(out_score, b->state + (size_t)F_SCORE * b->n, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (win_host) CUDA_TRY(cudaMemcpyAsync(out_step_of_win, b->state + (size_t)F_WIN_STEP * b->n, (size_t)b->n * 4, cudaMemcpyDeviceToHost, b->stream));
+    if (score_host || win_host || dp != params) CUDA_TRY(cudaStreamSynchronize(b->stream));
+    return PRL_OK;
+}
+
 int prl_batch_trajectory(prl_batch* b, int64_t n, const uint8_t* genomes, int32_t genome_len, int32_t repeat_move,
                          int32_t number_of_steps, float* out_state, float* out_distance, uint8_t* out_won) {
     if (!b || n <= 0 || genome_len < 0 || (genome_len > 0 && !genomes) || repeat_move < 1 || number_of_steps < 0) {

@@ -1510,6 +1510,63 @@ struct Stepper {
         return best;
     }
 
+    // ---- Observation for policies evaluated on the device: what Agent::get_move(&mut self,
+    // &Environment) (algorithm.rs:9) can read between two steps -- every body through
+    // rigid_body_set() (common.rs:201-211), the ground-contact scan Environment::step itself makes
+    // from narrow_phase / collider_set() (common.rs:223-244), distance_to_goals() (common.rs:175-195):
+    //   obs[9 b + 0..8]   body b: x, y, cos, sin, vx, vy, angvel, sleep timer, sleeping (0/1)
+    //   obs[9 nb + 0]     on_ground: 1 if the player has a floor contact (common.rs:244), else 0
+    //   obs[9 nb + 1]     number of floor contacts
+    //   obs[9 nb + 2]     1 if the player has an active contact with a pushable block, else 0
+    //   obs[9 nb + 3]     distance_to_goals() in editor pixels (+inf without goals)
+    // Call after detect_pending(). Before the first step the narrow phase is empty, so
+    // the contact entries are 0 then.
+    static constexpr int kObsExtra = 4;
+    PRL_D int floor_contact_count() const {
+        if (gs_n >= 0) return gs_n;
+        const float ly = e.y[0] - W.lower_off;
+        int nfc = 0;
+#pragma unroll 1
+        for (int it = it_begin(); it_ok(it); it = it_next(it)) {
+            const int slot = it_slot(it);
+            if (pair_of(slot) >= W.n_player_pairs) break;
+            const int ns = ns_of(slot);
+            const f4 s0 = k.sc[slot][0], s1 = k.sc[slot][1];
+            if (ns > 0 && (s0.w - ly) / W.radius < -0.707f) ++nfc;
+            if (ns > 1 && (s1.z - ly) / W.radius < -0.707f) ++nfc;
+        }
+        return nfc;
+    }
+    PRL_D bool touches_pushable_block() const {
+        if (NB == 1) return false;
+#pragma unroll 1
+        for (int it = it_begin(); it_ok(it); it = it_next(it)) {
+            const int slot = it_slot(it);
+            const int p = pair_of(slot);
+            if (p >= W.n_player_pairs) break;
+            if (ns_of(slot) > 0 && info_b2(W.pair_info[p]) >= 0) return true;
+        }
+        return false;
+    }
+    PRL_D void observe(float* obs) const {
+        const int nb = W.n_bodies;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (b < nb) {
+                float* o = obs + 9 * b;
+                o[0] = e.x[b]; o[1] = e.y[b]; o[2] = e.c[b]; o[3] = e.s[b]; o[4] = e.vx[b]; o[5] = e.vy[b];
+                o[6] = e.w[b]; o[7] = e.timer[b]; o[8] = (float)((e.sleeping >> b) & 1u);
+            }
+        }
+        const bool before_first_step = first_step || pend_all || (e.flags & FLAG_FRESH) != 0;
+        const int nfc = before_first_step ? 0 : floor_contact_count();
+        float* x = obs + 9 * nb;
+        x[0] = nfc > 0 ? 1.0f : 0.0f;
+        x[1] = (float)nfc;
+        x[2] = (!before_first_step && touches_pushable_block()) ? 1.0f : 0.0f;
+        x[3] = distance_to_goals();
+    }
+
     // Environment::step (common.rs:215-340) in three parts, so that the collision detection has
     // one call site and the warp can agree on the shape of its row storage between the halves (every
     // lane of the warp takes part in that vote, including lanes whose rollout has ended):
@@ -1557,5 +1614,36 @@ struct Stepper {
         return finish_step(0, 1);  // a single lane owns the planes
     }
 };
+
+// Policy of the observation-driven rollout (prl_kernels.cuh policy_rollout_kernel; layout in include/prl.h)
+constexpr int kMaxObs = 9 * MAXB + 4;
+constexpr int kMaxHidden = 32;
+PRL_D int policy_obs_dim(int n_bodies) { return 9 * n_bodies + 4; }
+PRL_D int policy_num_params(int n_bodies, int hidden) { return hidden * (policy_obs_dim(n_bodies) + 1) + 3 * (hidden + 1); }
+
+PRL_D uint32_t policy_move(const float* theta, int64_t n, int64_t a, int hidden, int D, const float* obs) {
+    float h[kMaxHidden];
+    const float* w = theta + a;
+#pragma unroll 1
+    for (int j = 0; j < hidden; ++j) {
+        const float* row = w + (int64_t)j * (D + 1) * n;
+        float acc = row[(int64_t)D * n];
+#pragma unroll 4
+        for (int i = 0; i < D; ++i) acc = acc + row[(int64_t)i * n] * obs[i];
+        h[j] = fmaxf(acc, 0.0f);
+    }
+    uint32_t mv = 0;
+    const float* w2 = w + (int64_t)hidden * (D + 1) * n;
+#pragma unroll 1
+    for (int k = 0; k < 3; ++k) {
+        const float* row = w2 + (int64_t)k * (hidden + 1) * n;
+        float acc = row[(int64_t)hidden * n];
+#pragma unroll 4
+        for (int j = 0; j < hidden; ++j) acc = acc + row[(int64_t)j * n] * h[j];
+        if (acc > 0.0f) mv |= 1u << k;
+    }
+    return mv;
+}
+
 
 }  // namespace prl

@@ -442,6 +442,89 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     if (out_win) out_win[i] = win_step;
 }
 
+// ---- Closed-loop agents evaluated inside the fused rollout: the batched form of
+// Agent::get_move(&mut self, &Environment) (algorithm.rs:8-11) for a small per-agent MLP.
+// Observation = Stepper::observe (bodies, ground-contact scan of common.rs:223-244, distance to the
+// goals), D = 9 n_bodies + 4 values. Policy of agent a, parameters theta[p * n + a] (parameter-major,
+// so a warp reads consecutive agents' copies of one parameter in one transaction):
+//   h_j   = max(b1_j + sum_i W1[j][i] obs_i, 0)      j < hidden      p = j (D + 1) + i, bias at i = D
+//   out_k = b2_k + sum_j W2[k][j] h_j                 k < 3           p = hidden (D + 1) + k (hidden + 1) + j
+//   Move  = (left, right, up) = (out_0 > 0, out_1 > 0, out_2 > 0)
+// Sums run left to right in f32 without contraction, so the CPU oracle evaluates the same bits.
+// The GA-style fitness rollout (main.rs:44-70 with repeat_move = 1) driven by the policy: every step
+// mv = policy(observation), Environment::step(mv), score = min distance; early_exit: break on win.
+template <int NB, class WT>
+__global__ void __launch_bounds__(kBlock, NB > 2 ? 5 : 6) policy_rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+                                                                                 const float* __restrict__ theta, int hidden, int number_of_steps,
+                                                                                 int early_exit, float* __restrict__ out_score,
+                                                                                 int32_t* __restrict__ out_win, int* __restrict__ overflow) {
+    using Sim = SimOf<NB, WT>;
+    __shared__ WT W;
+    __shared__ __align__(16) unsigned char row_pool[(kBlock / 32) * Sim::kWarpBytes + Sim::kPoolPad];
+    stage_world(&W, dw);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    if (!live) i = n - 1;
+    Env<NB> e;
+    Contacts<> ct;
+    env_init(W, e);
+    Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
+    float score = __int_as_float(0x7f800000);
+    int win_step = -1, steps = 0, t = 0;
+    const int D = policy_obs_dim(W.n_bodies);
+#pragma unroll 1
+    while (true) {
+        sim.detect_pending();
+        if (warp_all(!(t < number_of_steps))) break;  // the warp votes on its row storage every step: lanes leave together
+        const bool run = t < number_of_steps;
+        uint32_t mv = 0;
+        if (run) {
+            float obs[kMaxObs];
+            sim.observe(obs);
+            mv = policy_move(theta, n, i, hidden, D, obs);
+        }
+        const int need = run ? sim.begin_step(mv) : 0;
+        solve_in_rounds<Sim>(run, need, [&](int entry, int stride) {
+            float d = sim.finish_step(entry, stride);
+            ++steps;
+            ++t;
+            score = fminf(score, d);
+            const bool won = (e.flags & FLAG_WON) != 0;
+            if (won && win_step < 0) win_step = steps;
+            if (won && early_exit) t = number_of_steps;
+        });
+    }
+    if (!live) return;
+    if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);
+    env_store(W, e, ct, st, n, i);
+    st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
+    st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
+    st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
+    if (out_score) out_score[i] = score;
+    if (out_win) out_win[i] = win_step;
+}
+
+// Observation of the stored batch (layout of Stepper::observe): n x D floats
+template <int NB, class WT>
+__global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) observation_kernel(const DevWorld* __restrict__ dw, const uint32_t* __restrict__ st, int64_t n,
+                                                                             float* __restrict__ out) {
+    using Sim = SimOf<NB, WT>;
+    __shared__ WT W;
+    __shared__ __align__(16) unsigned char row_pool[(kBlock / 32) * Sim::kWarpBytes + Sim::kPoolPad];
+    stage_world(&W, dw);
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Env<NB> e;
+    Contacts<> ct;
+    env_load(W, e, ct, st, n, i);
+    Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
+    sim.refresh_solver_contacts();
+    float obs[kMaxObs];
+    sim.observe(obs);
+    const int D = policy_obs_dim(W.n_bodies);
+    for (int q = 0; q < D; ++q) out[i * D + q] = obs[q];
+}
+
 // Replay (train.rs:132-159): n fresh environments each play a GeneticAgent (main.rs:276-284) for
 // number_of_steps steps; every body's state, the distance to the goals and won() are recorded
 // after every step. out_state: steps x n x n_bodies x 9 (layout of gather_state_kernel).

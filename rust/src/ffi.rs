@@ -91,6 +91,11 @@ extern "C" {
     pub fn prl_batch_rollout_info(b: *mut prl_batch, out_score: *mut f32, out_step_of_win: *mut i32, out_steps: *mut i32) -> c_int;
     pub fn prl_batch_trajectory(b: *mut prl_batch, n: i64, genomes: *const u8, genome_len: i32, repeat_move: i32, number_of_steps: i32,
                                 out_state: *mut f32, out_distance: *mut f32, out_won: *mut u8) -> c_int;
+    pub fn prl_batch_observation_dim(b: *const prl_batch) -> i32;
+    pub fn prl_batch_get_observation(b: *mut prl_batch, out: *mut f32) -> c_int;
+    pub fn prl_policy_num_params(b: *const prl_batch, hidden: i32) -> i32;
+    pub fn prl_batch_rollout_policy(b: *mut prl_batch, params: *const f32, hidden: i32, number_of_steps: i32, early_exit: i32,
+                                    out_score: *mut f32, out_step_of_win: *mut i32) -> c_int;
     pub fn prl_batch_sync(b: *mut prl_batch) -> c_int;
     pub fn prl_batch_launch_count(b: *const prl_batch) -> i64;
     pub fn prl_batch_state_bytes(b: *const prl_batch) -> i64;

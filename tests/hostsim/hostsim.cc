@@ -100,6 +100,42 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
     return score;
 }
 
+// the policy rollout of prl_kernels.cuh policy_rollout_kernel for one environment (theta: this
+// agent's parameters, parameter p at theta[p * stride]); optionally records every observation
+template <int NB, int PR, class WT>
+static float policy_rollout(const WT& W, const float* theta, long stride, int hidden, int number_of_steps, int early_exit,
+                            float* obs_out, int* win_out, int* steps_out, int* overflow) {
+    static Env<NB> e;
+    static Contacts<> k;
+    init_env(W, e);
+    memset(&k, 0, sizeof k);
+    using Sim = Stepper<NB, MAXC, WT, PR>;
+    alignas(16) static unsigned char pool[Sim::kWarpBytes + Sim::kPoolPad];
+    Sim sim(W, e, k, pool);
+    float score = INFINITY;
+    int win = -1, steps = 0;
+    const int D = policy_obs_dim(W.n_bodies);
+    for (int t = 0; t < number_of_steps; ++t) {
+        sim.detect_pending();
+        float obs[kMaxObs];
+        sim.observe(obs);
+        if (obs_out) memcpy(obs_out + (size_t)t * D, obs, sizeof(float) * D);
+        uint32_t mv = policy_move(theta, stride, 0, hidden, D, obs);
+        sim.begin_step(mv);
+        float d = sim.finish_step(0, 1);
+        ++steps;
+        score = fminf(score, d);
+        bool won = (e.flags & FLAG_WON) != 0;
+        if (won && win < 0) win = steps;
+        if (won && early_exit) break;
+    }
+    sim.detect_pending();
+    *win_out = win;
+    *steps_out = steps;
+    *overflow = (e.flags & FLAG_OVERFLOW) ? 1 : 0;
+    return score;
+}
+
 // host copy of the kernels' stage_world(): compact the full-size tables into WT's capacities
 template <class WT>
 static void copy_world(WT& d, const DevWorld& s) {
@@ -151,6 +187,29 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
         *score = small_pool ? rollout<1, 4>(W, HS_ARGS) : rollout<1, 8>(W, HS_ARGS);
     } else {
         *score = small_pool ? rollout<MAXB, 4>(W, HS_ARGS) : rollout<MAXB, 8>(W, HS_ARGS);
+    }
+#undef HS_ARGS
+    return 0;
+}
+
+extern "C" int hs_policy_rollout(const char* json, size_t len, const float* theta, long stride, int hidden, int number_of_steps,
+                                 int early_exit, float* obs_out, float* score, int* win, int* steps, int* overflow) {
+    prl_world w;
+    int rc = parse_world_json(json, len, &w);
+    if (rc == PRL_OK) rc = build_dev_world(&w);
+    if (rc != PRL_OK) return rc;
+    const DevWorld& W = w.dev;
+#define HS_ARGS theta, stride, hidden, number_of_steps, early_exit, obs_out, win, steps, overflow
+    if (world_fits<DevWorldSmall>(W)) {
+        static DevWorldSmall S;
+        copy_world(S, W);
+        if (W.n_bodies == 1) *score = policy_rollout<1, 8>(S, HS_ARGS);
+        else if (W.n_bodies == 2) *score = policy_rollout<2, 9>(S, HS_ARGS);
+        else *score = policy_rollout<MAXB, 8>(S, HS_ARGS);
+    } else if (W.n_bodies == 1) {
+        *score = policy_rollout<1, 8>(W, HS_ARGS);
+    } else {
+        *score = policy_rollout<MAXB, 8>(W, HS_ARGS);
     }
 #undef HS_ARGS
     return 0;

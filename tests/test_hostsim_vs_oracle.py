@@ -141,3 +141,45 @@ def test_random_worlds_bit_exact(seed):
         o = oracle_traj(world, g, 20, 600)
         assert not np.isnan(o).any()
         assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
+
+
+def host_policy_rollout(world, theta_col, hidden, steps, early_exit):
+    """theta_col: (P, n) parameter-major array and a column index -> the host build of the policy rollout."""
+    theta, col = theta_col
+    js = json.dumps(world).encode()
+    hs = hostsim()
+    hs.hs_policy_rollout.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    D = 9 * n_bodies_of(world) + 4
+    obs = np.zeros((steps, D), np.float32)
+    sc, w, st, ov = C.c_float(), C.c_int(), C.c_int(), C.c_int()
+    rc = hs.hs_policy_rollout(js, len(js), theta.ctypes.data + 4 * col, theta.shape[1], hidden, steps, int(early_exit), obs.ctypes.data,
+                              C.byref(sc), C.byref(w), C.byref(st), C.byref(ov))
+    assert rc == 0 and ov.value == 0
+    return obs[:st.value], np.float32(sc.value), w.value, st.value
+
+
+@pytest.mark.parametrize("name", ["right", "jump", "push", "stack"])
+def test_policy_rollout_and_observation_bit_exact(name):
+    """The device logic of the observation-driven rollout (Stepper::observe + policy_move, host build)
+    against the oracle's independent restatement: every observation of every step, the moves that
+    follow from them (through the trajectories), scores and steps of win."""
+    from oracle import binding as oracle
+    world = world_dict(name) if name in WORLDS else edge_case_worlds()[name]
+    nb = n_bodies_of(world)
+    D, hidden, n, steps = 9 * nb + 4, 8, 3, 300
+    P = hidden * (D + 1) + 3 * (hidden + 1)
+    theta = np.random.Generator(np.random.Philox(31)).standard_normal((P, n)).astype(np.float32)
+    for early in (True, False):
+        rs, rw, _ = oracle.rollout_policy_batch(world, theta, hidden, steps, early, n_threads=2)
+        for a in range(n):
+            obs, sc, win, run = host_policy_rollout(world, (theta, a), hidden, steps, early)
+            assert sc.view(np.uint32) == rs[a].view(np.uint32) and win == rw[a]
+            if not early:
+                env = OracleEnv(world)
+                lib = oracle.lib()
+                for t in range(run):
+                    ref = env.observation()
+                    assert np.array_equal(obs[t].view(np.uint32), ref.view(np.uint32)), (a, t)
+                    mv = lib.orc_policy_move(theta.ctypes.data + 4 * a, n, hidden, D, ref.ctypes.data)
+                    env.step(mv)

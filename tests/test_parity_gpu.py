@@ -342,3 +342,74 @@ def test_random_worlds_match_oracle(seed):
         for t in range(steps):
             o.step(int(genomes[i][t // repeat]))
         assert np.array_equal(bits(st[i]), bits(o.state()))
+
+
+def policy_params(env, n, hidden, seed, scale=1.0):
+    """Random per-agent perceptrons whose moves actually vary with the observation."""
+    P = env.policy_num_params(hidden)
+    rng = np.random.Generator(np.random.Philox(seed))
+    return (rng.standard_normal((P, n)) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("name", ["right", "jump", "push"])
+def test_observation_matches_oracle(name):
+    """prl_batch_get_observation after 0, 1 and many steps: body state, on_ground / floor contacts /
+    touching-a-pushable-block (the scan of common.rs:223-244), distance to the goals."""
+    n, steps, repeat = 24, 240, 8
+    genomes = random_genomes(n, steps // repeat, 57)
+    genomes[0] = 0
+    genomes[1] = 2
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text(name)), n)
+    oracles = [OracleEnv(world_dict(name)) for _ in range(n)]
+    assert env.observation_dim == 9 * env.n_bodies + 4
+    seen_ground, seen_touch = False, False
+    for t in range(steps + 1):
+        if t in (0, 1, 2, 3) or t % 13 == 0 or t == steps:
+            obs = env.observation()
+            ref = np.stack([o.observation() for o in oracles])
+            assert np.array_equal(bits(obs), bits(ref)), f"after {t} steps"
+            seen_ground |= bool(obs[:, 9 * env.n_bodies].any())
+            seen_touch |= bool(obs[:, 9 * env.n_bodies + 2].any())
+            if t == 0:
+                assert not obs[:, 9 * env.n_bodies:9 * env.n_bodies + 3].any()  # the narrow phase is empty before the first step
+        if t < steps:
+            mv = np.ascontiguousarray(genomes[:, t // repeat])
+            env.step(mv)
+            for i, o in enumerate(oracles):
+                o.step(int(mv[i]))
+    assert seen_ground and (seen_touch or name != "push")
+
+
+@pytest.mark.parametrize("name,hidden", [("right", 4), ("jump", 16), ("push", 16), ("push", 32)])
+def test_policy_rollout_inside_the_kernel_matches_oracle(name, hidden):
+    """Agent::get_move evaluated in the fused rollout: a per-agent perceptron on the observation,
+    every step, against the oracle driven by the same parameters -- bit for bit, both early-exit modes."""
+    n, steps = 300, 500
+    env = prl.BatchedEnvironment(prl.World.from_json(world_text(name)), n)
+    params = policy_params(env, n, hidden, 1000 + hidden)
+    for early in (True, False):
+        score, win = env.rollout_policy(params, hidden, steps, early_exit=early)
+        env.sync()
+        rs, rw, rsteps = oracle.rollout_policy_batch(world_dict(name), params, hidden, steps, early, n_threads=os.cpu_count())
+        assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
+        assert int(env.rollout_info()[2].sum()) == rsteps
+    # the policies are not trivial: the population plays several different moves
+    assert len(np.unique(bits(score))) > n // 4
+
+
+def test_policy_rollout_device_buffers_and_edge_world():
+    import torch
+    world = edge_case_worlds()["stack"]  # three pushable blocks: the general kernel variant, 40 observation values
+    n, hidden, steps = 130, 8, 300
+    env = prl.BatchedEnvironment(prl.World.from_json(json.dumps(world)), n, stream=torch.cuda.current_stream().cuda_stream)
+    assert env.observation_dim == 9 * 4 + 4
+    params = policy_params(env, n, hidden, 5)
+    dp = torch.from_numpy(params).cuda()
+    ds = torch.empty(n, dtype=torch.float32, device="cuda")
+    dw = torch.empty(n, dtype=torch.int32, device="cuda")
+    env.rollout_policy(dp, hidden, steps, early_exit=False, out_score=ds, out_step_of_win=dw)
+    torch.cuda.synchronize()
+    rs, rw, _ = oracle.rollout_policy_batch(world, params, hidden, steps, False, n_threads=os.cpu_count())
+    assert np.array_equal(bits(ds.cpu().numpy()), bits(rs)) and np.array_equal(dw.cpu().numpy(), rw)
+    with pytest.raises(prl.PrlError):
+        env.rollout_policy(params, 33, steps)  # hidden > 32
