@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
 // The GA-style fitness rollout (main.rs:44-70 with repeat_move = 1) driven by the policy: every step
 // mv = policy(observation), Environment::step(mv), score = min distance; early_exit: break on win.
 template <int NB, class WT>
-__global__ void __launch_bounds__(kBlock, NB > 2 ? 5 : 6) policy_rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+__global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) policy_rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                                                  const float* __restrict__ theta, int hidden, int number_of_steps,
                                                                                  int early_exit, float* __restrict__ out_score,
                                                                                  int32_t* __restrict__ out_win, int* __restrict__ overflow) {

