@@ -324,8 +324,10 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
     int32_t* dw = win_host ? nullptr : out_step_of_win;
     {
         // one 448-thread block per SM once the batch can fill half the SMs that way, else 64-thread
-        // blocks. Only the kernels with pushable blocks gain (their step is twice the code; the
-        // single-body kernels measured 10-13 % slower with the per-step barrier).
+        // blocks. Only the kernels with pushable blocks gain (their step is twice the code). Single-body
+        // kernels measured 10-13 % slower in lock step, and 1.5 % slower with SM-wide blocks that only
+        // meet to regroup (round 2: sorting the few walking players of a random population into their
+        // own warps does not shorten those warps' dependent chain, which is what bounds the kernel).
         const bool big = b->n >= (int64_t)b->sm_count * kBigBlock / 2;
         // a population too small to give every SM a 64-thread block (config C2: 4096 agents) runs one
         // warp per block, so that it spreads over twice as many SMs: such a rollout is bound by the

@@ -212,24 +212,26 @@ PRL_D void face_face_contacts(Manifold& m, const Iso& pos12, v2 s1a, v2 s1b, v2 
     if (r1b < r1a) { float t = r1a; r1a = r1b; r1b = t; v2 p = s1a; s1a = s1b; s1b = p; }
     if (r2b < r2a) { float t = r2a; r2a = r2b; r2b = t; v2 p = s2a; s2a = s2b; s2b = p; }
     if (r2a > r1b || r1a > r2b) return;
+    // Both ends of the overlap: the end that lies inside the other segment is interpolated on it,
+    // bc = (r - ra) * inv0(rb - ra). One expression (and one division) per end; which segment is
+    // interpolated is a select of the operands, the arithmetic is parry's in either case.
+    const float inv1 = inv0(r1b - r1a), inv2 = inv0(r2b - r2a);
     v2 c0, c1, c2, c3;
-    if (r2a > r1a) {
-        float bc = (r2a - r1a) * inv0(r1b - r1a);
-        c0 = s1a + (s1b - s1a) * bc;
-        c1 = s2a;
-    } else {
-        float bc = (r1a - r2a) * inv0(r2b - r2a);
-        c0 = s1a;
-        c1 = s2a + (s2b - s2a) * bc;
+    {
+        const bool on1 = r2a > r1a;  // the low end of segment 2 falls inside segment 1
+        const float bc = on1 ? (r2a - r1a) * inv1 : (r1a - r2a) * inv2;
+        const v2 base = on1 ? s1a : s2a, span = on1 ? s1b - s1a : s2b - s2a;
+        const v2 ip = base + span * bc;
+        c0 = on1 ? ip : s1a;
+        c1 = on1 ? s2a : ip;
     }
-    if (r2b < r1b) {
-        float bc = (r2b - r1a) * inv0(r1b - r1a);
-        c2 = s1a + (s1b - s1a) * bc;
-        c3 = s2b;
-    } else {
-        float bc = (r1b - r2a) * inv0(r2b - r2a);
-        c2 = s1b;
-        c3 = s2a + (s2b - s2a) * bc;
+    {
+        const bool on1 = r2b < r1b;  // the high end of segment 2 falls inside segment 1
+        const float bc = on1 ? (r2b - r1a) * inv1 : (r1b - r2a) * inv2;
+        const v2 base = on1 ? s1a : s2a, span = on1 ? s1b - s1a : s2b - s2a;
+        const v2 ip = base + span * bc;
+        c2 = on1 ? ip : s1b;
+        c3 = on1 ? s2b : ip;
     }
     m.p1[0] = c0;
     m.p2[0] = xform_inv(pos12, c1);
@@ -288,12 +290,14 @@ PRL_COLD Manifold contact_cuboid_cuboid_full(Iso pos12, v2 he1, v2 he2, float pr
 // frame: exact closest-feature enumeration (2 segment endpoints vs the box, 4 box corners vs the
 // segment; fixed order, strict '<'). parry reaches the same pair with GJK up to its tolerance.
 // Returns false if the segment touches the box.
+// (Rolled loops on purpose: this runs for a few lanes of nearly every warp-step, so what it costs is
+// instruction-cache footprint, not issue slots -- profiles/r02_experiments.md.)
 PRL_D bool segment_box_closest(v2 a, v2 b, v2 he, float& u_out, v2& q_out) {
     v2 d = b - a;
     {
         float t0 = 0.0f, t1 = 1.0f;
         bool hit = true;
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 2; ++i) {
             float av = i == 0 ? a.x : a.y, dv = i == 0 ? d.x : d.y, hv = i == 0 ? he.x : he.y;
             if (hit) {
@@ -313,28 +317,55 @@ PRL_D bool segment_box_closest(v2 a, v2 b, v2 he, float& u_out, v2& q_out) {
     }
     float best = kFltMax, bu = 0.0f;
     v2 bq = V(0.0f, 0.0f);
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-        v2 p = e == 0 ? a : b;
-        v2 q = V(fminf(fmaxf(p.x, -he.x), he.x), fminf(fmaxf(p.y, -he.y), he.y));
-        v2 r = q - p;
+    const float idd2 = inv0(dot(d, d));
+    // candidates in fixed order with strict '<': the two segment endpoints against the box, then the
+    // four box corners (-,-), (+,-), (+,+), (-,+) against the segment
+#pragma unroll 1
+    for (int c = 0; c < 6; ++c) {
+        v2 q, r;
+        float u;
+        if (c < 2) {
+            v2 p = c == 0 ? a : b;
+            q = V(fminf(fmaxf(p.x, -he.x), he.x), fminf(fmaxf(p.y, -he.y), he.y));
+            r = q - p;
+            u = c == 0 ? 0.0f : 1.0f;
+        } else {
+            const int kc = c - 2;
+            q = V((kc == 1 || kc == 2) ? he.x : -he.x, (kc >= 2) ? he.y : -he.y);
+            u = dot(q - a, d) * idd2;
+            u = fminf(fmaxf(u, 0.0f), 1.0f);
+            v2 ps = a + d * u;
+            r = q - ps;
+        }
         float dd = dot(r, r);
-        if (dd < best) { best = dd; bu = e == 0 ? 0.0f : 1.0f; bq = q; }
-    }
-    float dd2 = dot(d, d);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        v2 cn = V((k == 1 || k == 2) ? he.x : -he.x, (k >= 2) ? he.y : -he.y);
-        float u = dot(cn - a, d) * inv0(dd2);
-        u = fminf(fmaxf(u, 0.0f), 1.0f);
-        v2 ps = a + d * u;
-        v2 r = cn - ps;
-        float dd = dot(r, r);
-        if (dd < best) { best = dd; bu = u; bq = cn; }
+        if (dd < best) { best = dd; bu = u; bq = q; }
     }
     u_out = bu;
     q_out = bq;
     return true;
+}
+
+// parry's EPA branch of contact_manifold_pfm_pfm: the capsule's inner segment is inside the box.
+// Minimum face penetration of the deeper endpoint (unreachable at this game's speeds except by a
+// level that spawns the player inside a block). Returns (p1 | p2_1) and writes dir.
+struct InsideBox { v2 p1, p2_1, dir; };
+PRL_COLD InsideBox capsule_inside_box(Iso pos12, v2 a2, v2 b2, v2 he2) {
+    float best = kFltMax;
+    v2 nb = V(0.0f, 1.0f), pe = a2, qf = a2;
+#pragma unroll 1
+    for (int f = 0; f < 4; ++f) {
+        v2 nf = f == 0 ? V(1.0f, 0.0f) : f == 1 ? V(-1.0f, 0.0f) : f == 2 ? V(0.0f, 1.0f) : V(0.0f, -1.0f);
+        float hf = f < 2 ? he2.x : he2.y;
+        float da = dot(a2, nf), db = dot(b2, nf);
+        v2 e = da < db ? a2 : b2;
+        float depth = hf - fminf(da, db);
+        if (depth < best) { best = depth; nb = nf; pe = e; qf = e + nf * depth; }
+    }
+    InsideBox r;
+    r.p1 = xform(pos12, pe);
+    r.p2_1 = xform(pos12, qf);
+    r.dir = -rot(pos12.c, pos12.s, nb);
+    return r;
 }
 
 // parry contact_manifold_pfm_pfm with pfm1 = the capsule's segment (border radius r) and
@@ -355,21 +386,8 @@ PRL_COLD Manifold contact_capsule_cuboid_full(Iso pos12, float radius, float hh,
         if (n > total_prediction) return m;
         dir = V(dp.x / n, dp.y / n);
     } else {
-        // inner segment inside the box (parry: EPA): minimum face penetration of the deeper endpoint
-        float best = kFltMax;
-        v2 nb = V(0.0f, 1.0f), pe = a2, qf = a2;
-#pragma unroll
-        for (int f = 0; f < 4; ++f) {
-            v2 nf = f == 0 ? V(1.0f, 0.0f) : f == 1 ? V(-1.0f, 0.0f) : f == 2 ? V(0.0f, 1.0f) : V(0.0f, -1.0f);
-            float hf = f < 2 ? he2.x : he2.y;
-            float da = dot(a2, nf), db = dot(b2, nf);
-            v2 e = da < db ? a2 : b2;
-            float depth = hf - fminf(da, db);
-            if (depth < best) { best = depth; nb = nf; pe = e; qf = e + nf * depth; }
-        }
-        p1 = xform(pos12, pe);
-        p2_1 = xform(pos12, qf);
-        dir = -rot(pos12.c, pos12.s, nb);
+        const InsideBox in = capsule_inside_box(pos12, a2, b2, he2);
+        p1 = in.p1; p2_1 = in.p2_1; dir = in.dir;
     }
     v2 n2 = rot_inv(pos12.c, pos12.s, -dir);
     v2 f2a, f2b;

@@ -330,9 +330,6 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     const int main_steps = genome_len * repeat_move;
     const int total = main_steps + number_of_steps % repeat_move;
     int g = 0, rep = 0, t = 0, iter = 0;
-#if defined(PRL_REGROUP_AVG)
-    int acc_need = 0;
-#endif
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
     int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes + Sim::kPoolPad);  // only if BLOCK == kBigBlock
 #if defined(PRL_PHASE_TIMING)
@@ -347,6 +344,24 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
         const bool all_done = __syncthreads_and(!(t < total));
         PRL_TICK_K(8);
         if (all_done) break;
+#if defined(PRL_ICACHE_SCATTER)
+        {
+            // measurement builds only: PRL_ICACHE_SCATTER chunks of code, each reached by a taken branch
+            // over 7 never-executed instructions, i.e. ~160 B of NON-sequential instruction footprint per
+            // chunk (profiles/r02_experiments.md)
+            float p0 = score;
+#pragma unroll
+            for (int q = 0; q < PRL_ICACHE_SCATTER; ++q) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %1, -77;\n\t@p bra SKIP%=;\n\t"
+                    "add.f32 %0, %0, 0f3F800000;\n\tmul.f32 %0, %0, 0f3F800001;\n\tadd.f32 %0, %0, 0f3F800002;\n\t"
+                    "mul.f32 %0, %0, 0f3F800003;\n\tadd.f32 %0, %0, 0f3F800004;\n\tmul.f32 %0, %0, 0f3F800005;\n\t"
+                    "add.f32 %0, %0, 0f3F800006;\n\t"
+                    "SKIP%=:\n\tadd.f32 %0, %0, 0f3F800000;\n\t}" : "+f"(p0) : "r"(number_of_steps));
+            }
+            if (p0 == -12345.0f) score = p0;
+        }
+#endif
 #if defined(PRL_ICACHE_PAD)
         {
             // measurement builds only: PRL_ICACHE_PAD KB of straight-line code executed once per step, to
@@ -374,13 +389,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
                 st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;
                 st[(int64_t)F_ROLL * n + i] = (uint32_t)t;
             }
-#if defined(PRL_REGROUP_AVG)
-            const int avg2 = (2 * acc_need + kRegroupEvery / 2) / kRegroupEvery;  // twice the mean rows per step since the last regroup
-            const int key = t < total ? 1 + (avg2 < 32 ? avg2 : 32) : 0;
-            acc_need = 0;
-#else
-            const int key = t < total ? 1 + (sim.need < 32 ? sim.need : 32) : 0;
-#endif
+            const int key = t < total ? 1 + (sim.need < 32 ? sim.need : 32) : 0;  // finished rollouts last
             if (threadIdx.x < kRegroupKeys) hist[threadIdx.x] = 0;
             __syncthreads();
             const int pos = atomicAdd(&hist[key], 1);
@@ -409,9 +418,6 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
         const bool run = t < total;
         const bool in_genes = t < main_steps;
         const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
-#if defined(PRL_REGROUP_AVG)
-        acc_need += need;
-#endif
         solve_in_rounds<Sim>(run, need, [&](int entry, int stride) {
             float d = sim.finish_step(entry, stride);
             ++steps;

@@ -19,6 +19,7 @@ sys.path.insert(0, ROOT)
 from bench import make_genomes  # noqa: E402
 
 STEPS, REPEAT = 2000, 20
+WORLD = os.environ.get("PRL_STUDY_WORLD", "push")
 
 
 def trace_chunk(args):
@@ -27,7 +28,7 @@ def trace_chunk(args):
     hs.hs_rollout.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                               C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     hs.hs_set_trace.argtypes = [C.c_void_p, C.c_long]
-    js = open(os.path.join(ROOT, "worlds", "push.json")).read().encode()
+    js = open(os.path.join(ROOT, "worlds", f"{WORLD}.json")).read().encode()
     genomes = make_genomes(65536, STEPS // REPEAT, 0xB200)[lo:hi]
     out = np.zeros((hi - lo, STEPS, 4), np.int32)
     sc, w, st, ov = C.c_float(), C.c_int(), C.c_int(), C.c_int()
@@ -41,7 +42,7 @@ def trace_chunk(args):
 def main():
     n_blocks = int(sys.argv[1]) if len(sys.argv) > 1 else 4
     n = n_blocks * 448
-    cache = f"/tmp/regroup_trace_{n}.npy"
+    cache = f"/tmp/regroup_trace_{WORLD}_{n}.npy"
     if os.path.exists(cache):
         tr = np.load(cache)
     else:

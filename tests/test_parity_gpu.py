@@ -211,13 +211,16 @@ def test_ragged_batch_on_the_448_thread_kernel():
     assert np.array_equal(bits(score), bits(rs[idx])) and np.array_equal(win, rw[idx])
 
 
-@pytest.mark.parametrize("which", ["stack", "posts8", "posts6"])
+@pytest.mark.parametrize("which", ["stack", "posts8", "posts6", "jump", "synth64"])
 def test_448_thread_kernel_variants_with_several_pushable_blocks(which):
     """`rollout_kernel<MAXB, DevWorldSmall, 448>` (a pile of three pushable blocks) and
     `rollout_kernel<MAXB, DevWorld, 448>` (a plank on 8 posts: 17+ candidate pairs, the general
     tables) are only launched for batches of >= 33152 environments; 6 posts is push's own variant
-    solving in rounds. Every environment is compared with the oracle (4096 distinct genomes)."""
-    world = {"stack": edge_case_worlds()["stack"], "posts8": many_supports_world(8), "posts6": many_supports_world(6)}[which]
+    solving in rounds; jump.json / the synthetic 64-obstacle world run the single-body 64-thread
+    variants at the same batch size.
+    Every environment is compared with the oracle (4096 distinct genomes)."""
+    world = {"stack": edge_case_worlds()["stack"], "posts8": many_supports_world(8), "posts6": many_supports_world(6),
+             "jump": world_dict("jump"), "synth64": synth_world()}[which]
     n, L, repeat, steps = 148 * 448 // 2 + 448, 20, 20, 400
     distinct = 4096
     genomes = np.ascontiguousarray(np.resize(random_genomes(distinct, L, 0x99 + len(which)), (n, L)))
