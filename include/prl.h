@@ -48,7 +48,7 @@ typedef enum {
 #define PRL_MOVE_UP 4u
 
 /* compiled limits */
-#define PRL_MAX_DYNAMIC 4     /* pushable blocks per world */
+#define PRL_MAX_DYNAMIC 7     /* pushable blocks per world (the per-environment sleeping mask has 8 bits: player + 7) */
 #define PRL_MAX_BLOCKS 128    /* fixed + pushable blocks per world */
 #define PRL_MAX_PAIRS 128     /* candidate collider pairs per world */
 #define PRL_MAX_GOALS 16

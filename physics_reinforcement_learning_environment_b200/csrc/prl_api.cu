@@ -43,10 +43,11 @@ inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBloc
 // Kernel variants: (bodies, world-table capacity). Small worlds (<= 15 blocks, the shipped
 // levels) with at most one pushable block get the compact tables and the 48-byte solver rows;
 // everything else runs the general variant.
-enum Variant { V1_SMALL, V2_SMALL, VN_SMALL, V1_BIG, VN_BIG };
+enum Variant { V1_SMALL, V2_SMALL, VN_SMALL, V1_BIG, VN_BIG, VX_BIG };
 Variant pick_variant(const DevWorld& w) {
     bool small = world_fits<DevWorldSmall>(w);
     if (w.n_bodies == 1) return small ? V1_SMALL : V1_BIG;
+    if (w.n_bodies > MIDB) return VX_BIG;  // 5 - 7 pushable blocks: body state no longer fits the register file, exact but slower
     if (small) return w.n_bodies == 2 ? V2_SMALL : VN_SMALL;
     return VN_BIG;
 }
@@ -54,8 +55,9 @@ Variant pick_variant(const DevWorld& w) {
     switch (variant) {                                                                                           \
         case V1_SMALL: KERNEL<1, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;               \
         case V2_SMALL: KERNEL<2, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;               \
-        case VN_SMALL: KERNEL<MAXB, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;            \
+        case VN_SMALL: KERNEL<MIDB, DevWorldSmall><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;            \
         case V1_BIG: KERNEL<1, DevWorld><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;                      \
+        case VN_BIG: KERNEL<MIDB, DevWorld><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;                   \
         default: KERNEL<MAXB, DevWorld><<<grid, kBlock, 0, stream>>>(__VA_ARGS__); break;                       \
     }
 
@@ -354,9 +356,10 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
                 else if (tiny) PRL_ROLLOUT(2, DevWorldSmall, kWarpBlock);
                 else PRL_ROLLOUT(2, DevWorldSmall, kBlock);
                 break;
-            case VN_SMALL: if (big) PRL_ROLLOUT(MAXB, DevWorldSmall, kBigBlock); else PRL_ROLLOUT(MAXB, DevWorldSmall, kBlock); break;
+            case VN_SMALL: if (big) PRL_ROLLOUT(MIDB, DevWorldSmall, kBigBlock); else PRL_ROLLOUT(MIDB, DevWorldSmall, kBlock); break;
             case V1_BIG: if (tiny) PRL_ROLLOUT(1, DevWorld, kWarpBlock); else PRL_ROLLOUT(1, DevWorld, kBlock); break;
-            default: if (big) PRL_ROLLOUT(MAXB, DevWorld, kBigBlock); else PRL_ROLLOUT(MAXB, DevWorld, kBlock); break;
+            case VN_BIG: if (big) PRL_ROLLOUT(MIDB, DevWorld, kBigBlock); else PRL_ROLLOUT(MIDB, DevWorld, kBlock); break;
+            default: PRL_ROLLOUT(MAXB, DevWorld, kBlock); break;
         }
 #undef PRL_ROLLOUT
         CUDA_TRY(le);

@@ -15,6 +15,7 @@ namespace prl {
 
 constexpr int MAXCOL = PRL_MAX_BLOCKS + 1;   // colliders: player + blocks
 constexpr int MAXB = PRL_MAX_DYNAMIC + 1;    // bodies: player + pushable blocks
+constexpr int MIDB = 5;                      // kernels keep the bodies in registers: variants for 1, 2, <= MIDB and <= MAXB bodies
 constexpr int MAXP = PRL_MAX_PAIRS;
 constexpr int MAXG = PRL_MAX_GOALS;
 constexpr int MAXC = PRL_MAX_CONTACTS;       // manifold slots per environment

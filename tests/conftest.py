@@ -84,6 +84,12 @@ def edge_case_worlds():
             fixed(5.0, -4.0, 200.0, 120.0), fixed(260.0, -80.0, 300.0, 40.0, 0.1), goal(330.0, -20.0, 60.0, 60.0)]},
         "three_goals": {"player_position": [-50.0, 0.0], "objects": [
             goal(-300.0, 10.0, 40.0, 40.0, 1.2), fixed(0.0, -50.0, 900.0, 40.0), goal(200.0, 20.0, -60.0, 90.0), goal(60.0, 120.0, 30.0, 30.0, -0.5)]},
+        # six pushable blocks (the reference has no limit, common.rs:127-146; the kernels keep up to 7 in
+        # one environment): two piles of two and two loose ones on a floor with a wall, the player dropped on a pile
+        "six_pushables": {"player_position": [-20.0, 150.0], "objects": [
+            fixed(0.0, -50.0, 1000.0, 40.0), dyn(-30.0, -10.0, 80.0, 40.0), dyn(-25.0, 32.0, 60.0, 40.0), fixed(330.0, 0.0, 40.0, 200.0),
+            dyn(120.0, -10.0, 50.0, 40.0), dyn(125.0, 28.0, 40.0, 30.0, 0.05), dyn(220.0, -15.0, 40.0, 30.0), dyn(-150.0, -12.0, 70.0, 36.0, -0.02),
+            goal(280.0, 0.0, 60.0, 60.0)]},
         "stack": {"player_position": [0.0, 160.0], "objects": [
             fixed(0.0, -50.0, 700.0, 40.0), dyn(0.0, -10.0, 120.0, 40.0), dyn(10.0, 35.0, 90.0, 40.0), dyn(-5.0, 80.0, 60.0, 40.0, 0.1),
             goal(250.0, 0.0, 70.0, 70.0)]},

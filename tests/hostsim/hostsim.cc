@@ -177,14 +177,16 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
     const bool small_pool = g_row_cap < 8;
     // the same variant choice as the library (prl_api.cu pick_variant): small worlds run with the
     // compact tables and slot == pair manifolds, the rest with the general tables
-    if (world_fits<DevWorldSmall>(W)) {
+    if (world_fits<DevWorldSmall>(W) && W.n_bodies <= MIDB) {
         static DevWorldSmall S;
         copy_world(S, W);
         if (W.n_bodies == 1) *score = small_pool ? rollout<1, 4>(S, HS_ARGS) : rollout<1, 8>(S, HS_ARGS);
         else if (W.n_bodies == 2) *score = small_pool ? rollout<2, 4>(S, HS_ARGS) : rollout<2, 9>(S, HS_ARGS);
-        else *score = small_pool ? rollout<MAXB, 4>(S, HS_ARGS) : rollout<MAXB, 8>(S, HS_ARGS);
+        else *score = small_pool ? rollout<MIDB, 4>(S, HS_ARGS) : rollout<MIDB, 8>(S, HS_ARGS);
     } else if (W.n_bodies == 1) {
         *score = small_pool ? rollout<1, 4>(W, HS_ARGS) : rollout<1, 8>(W, HS_ARGS);
+    } else if (W.n_bodies <= MIDB) {
+        *score = small_pool ? rollout<MIDB, 4>(W, HS_ARGS) : rollout<MIDB, 8>(W, HS_ARGS);
     } else {
         *score = small_pool ? rollout<MAXB, 4>(W, HS_ARGS) : rollout<MAXB, 8>(W, HS_ARGS);
     }
@@ -200,14 +202,16 @@ extern "C" int hs_policy_rollout(const char* json, size_t len, const float* thet
     if (rc != PRL_OK) return rc;
     const DevWorld& W = w.dev;
 #define HS_ARGS theta, stride, hidden, number_of_steps, early_exit, obs_out, win, steps, overflow
-    if (world_fits<DevWorldSmall>(W)) {
+    if (world_fits<DevWorldSmall>(W) && W.n_bodies <= MIDB) {
         static DevWorldSmall S;
         copy_world(S, W);
         if (W.n_bodies == 1) *score = policy_rollout<1, 8>(S, HS_ARGS);
         else if (W.n_bodies == 2) *score = policy_rollout<2, 9>(S, HS_ARGS);
-        else *score = policy_rollout<MAXB, 8>(S, HS_ARGS);
+        else *score = policy_rollout<MIDB, 8>(S, HS_ARGS);
     } else if (W.n_bodies == 1) {
         *score = policy_rollout<1, 8>(W, HS_ARGS);
+    } else if (W.n_bodies <= MIDB) {
+        *score = policy_rollout<MIDB, 8>(W, HS_ARGS);
     } else {
         *score = policy_rollout<MAXB, 8>(W, HS_ARGS);
     }

@@ -153,7 +153,7 @@ def test_json_ingest_follows_serde(text, n_objects):
 
 def test_capacity_limits_are_reported():
     blocks = [{"object": {"Block": {"fixed": False}}, "position": [60.0 * i, 0.0, 1.0], "scale": [20.0, 20.0], "rotation": 0.0}
-              for i in range(5)]
+              for i in range(8)]
     with pytest.raises(prl.PrlError) as e:
         prl.World.from_json(json.dumps({"player_position": [0, 0], "objects": blocks}))
     assert e.value.status == _lib.PRL_ERR_CAPACITY
