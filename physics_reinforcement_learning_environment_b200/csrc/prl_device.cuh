@@ -756,34 +756,30 @@ struct Stepper {
         const bool second_min = nfc == 2 && gs_x[1] < gs_x[0];
         const bool second_max = nfc == 2 && !(gs_x[1] < gs_x[0]);
         v2 player_impulse = V(0.0f, 0.0f);
-        // left / right: tangent impulse at the extreme floor contact (common.rs:249-295)
+        const float cnt = (float)nfc;
+        // The reference's three blocks -- left: tangent impulse at the min-x floor contact
+        // (common.rs:249-271), right: at the max-x one (:273-295), up: the jump impulse shared by all
+        // floor contacts (:297-310) -- as ONE loop over up to four impulse applications in that order
+        // (one copy of the code: the step is bound by its instruction footprint). Per application:
+        //   n = normalize(point - lower centre)
+        //   left  J = ( 0.003 n.y, -0.003 n.x)    right J = (-0.003 n.y, 0.003 n.x)    up J = -0.1 n / count
+        //   a dynamic contact body gets -J at the point; the player accumulates J
+        uint32_t todo = (mv & 3u) | ((mv & 4u) ? (nfc == 2 ? 12u : 4u) : 0u);
 #pragma unroll 1
-        for (int side = 0; side < 2; ++side) {
-            if (mv & (1u << side)) {
-                const bool second = side == 0 ? second_min : second_max;
-                v2 pt = second ? V(gs_x[1], gs_y[1]) : V(gs_x[0], gs_y[0]);
-                int body = second ? gs_b[1] : gs_b[0];
-                v2 n = pt - lower;
-                float len = sqrtf(n.x * n.x + n.y * n.y);
-                n = V(n.x / len, n.y / len);
-                v2 imp = side == 0 ? V(0.003f * n.y, -0.003f * n.x) : V(-0.003f * n.y, 0.003f * n.x);
-                if (NB > 1 && body >= 0) apply_impulse_at_point(body, -imp, pt);
-                player_impulse = player_impulse + imp;
-            }
-        }
-        if (mv & 4u) {  // up: the jump impulse is shared by all floor contacts (common.rs:297-310)
-            float cnt = (float)nfc;
-#pragma unroll 1
-            for (int k = 0; k < nfc; ++k) {
-                v2 pt = k == 0 ? V(gs_x[0], gs_y[0]) : V(gs_x[1], gs_y[1]);
-                int body = k == 0 ? gs_b[0] : gs_b[1];
-                v2 n = pt - lower;
-                float len = sqrtf(n.x * n.x + n.y * n.y);
-                n = V(n.x / len, n.y / len);
-                v2 imp = V(-0.1f * n.x / cnt, -0.1f * n.y / cnt);
-                if (NB > 1 && body >= 0) apply_impulse_at_point(body, -imp, pt);
-                player_impulse = player_impulse + imp;
-            }
+        for (; todo != 0; todo &= todo - 1) {
+            const int a = first_bit_from(todo, 0);
+            const bool second = a == 0 ? second_min : (a == 1 ? second_max : a == 3);
+            const v2 pt = second ? V(gs_x[1], gs_y[1]) : V(gs_x[0], gs_y[0]);
+            const int body = second ? gs_b[1] : gs_b[0];
+            v2 n = pt - lower;
+            const float len = sqrtf(n.x * n.x + n.y * n.y);
+            n = V(n.x / len, n.y / len);
+            const bool side = a < 2;
+            const float cx = a == 0 ? 0.003f : (a == 1 ? -0.003f : -0.1f), cy = a == 0 ? -0.003f : (a == 1 ? 0.003f : -0.1f);
+            v2 imp = V(cx * (side ? n.y : n.x), cy * (side ? n.x : n.y));
+            if (!side) imp = V(imp.x / cnt, imp.y / cnt);
+            if (NB > 1 && body >= 0) apply_impulse_at_point(body, -imp, pt);
+            player_impulse = player_impulse + imp;
         }
         apply_impulse(0, player_impulse);
     }
@@ -1262,7 +1258,8 @@ struct Stepper {
                 else if (NB == 2) {
                     ground_rows<true, 0>(ntb, jsplit, dlx, dly, da);
                     ground_rows<true, 1>(jsplit, nrows, dlx, dly, da);
-                } else ground_rows<true, -1>(ntb, nrows, dlx, dly, da);
+                }
+                else ground_rows<true, -1>(ntb, nrows, dlx, dly, da);
             } else {
                 if (NB > 1) {
 #pragma unroll 1
@@ -1272,7 +1269,8 @@ struct Stepper {
                 else if (NB == 2) {
                     ground_rows<false, 0>(ntb, jsplit, dlx, dly, da);
                     ground_rows<false, 1>(jsplit, nrows, dlx, dly, da);
-                } else ground_rows<false, -1>(ntb, nrows, dlx, dly, da);
+                }
+                else ground_rows<false, -1>(ntb, nrows, dlx, dly, da);
             }
         }
         PRL_TICK(6);
@@ -1344,7 +1342,7 @@ struct Stepper {
             // masks -- overlapping pairs, and (from the world's body -> pairs table) pairs with a
             // moved collider -- so its table look-ups overlap instead of waiting for each other
             uint32_t ov = 0;
-#pragma unroll 4
+#pragma unroll 2  // (4: -4 % on jump.json, the single-body kernels are bound by their instruction footprint)
             for (int p = 0; p < W.n_pairs; ++p) {
                 bool modified;
                 if (pair_overlaps(p, moved, all, bmnx, bmny, bmxx, bmxy, modified)) ov |= 1u << p;
@@ -1585,6 +1583,21 @@ struct Stepper {
         x[3] = distance_to_goals();
     }
 
+    // min over the goals of the SQUARED physics-space distance (the argument of distance_to_goals'
+    // sqrt): the fused rollout keeps the running minimum of this and takes one sqrt and one division at
+    // its end -- sqrt and the division by the scale are monotone, so min and win test commute with them
+    PRL_D float goal_distance_sq() const {
+        float best = f32_inf();
+#pragma unroll 1
+        for (int i = 0; i < W.n_goals; ++i) {
+            v2 d = V(e.x[0] - W.gx[i], e.y[0] - W.gy[i]);
+            float dx = fmaxf(fabsf(d.x * W.gxax[i] + d.y * W.gxay[i]) - W.ghw[i], 0.0f);
+            float dy = fmaxf(fabsf(d.x * W.gyax[i] + d.y * W.gyay[i]) - W.ghh[i], 0.0f);
+            best = fminf(best, dx * dx + dy * dy);  // (finite state: no NaN to propagate)
+        }
+        return best;
+    }
+
     // Environment::step (common.rs:215-340) in three parts, so that the collision detection has
     // one call site and the warp can agree on the shape of its row storage between the halves (every
     // lane of the warp takes part in that vote, including lanes whose rollout has ended):
@@ -1623,6 +1636,20 @@ struct Stepper {
         if (!(e.flags & FLAG_WON) && W.n_goals > 0 && d < 1e-7f) e.flags |= FLAG_WON;
         PRL_TICK(7);
         return d;
+    }
+    // finish_step for rollouts that only need the running minimum and the win latch: returns the
+    // squared distance; won() latches iff sqrt(q) / scale < 1e-7, i.e. iff q <= W.win_q
+    PRL_D float finish_step_sq(int first_entry, int entry_stride) {
+        pend_moved = solve_and_integrate(first_entry, entry_stride);
+        const float q = goal_distance_sq();
+        if (!(e.flags & FLAG_WON) && W.n_goals > 0 && q <= W.win_q) e.flags |= FLAG_WON;
+        PRL_TICK(7);
+        return q;
+    }
+    PRL_D float step_q(uint32_t mv) {  // host build
+        detect_pending();
+        begin_step(mv);
+        return finish_step_sq(0, 1);
     }
     // the whole step for one lane on its own (host build); call detect_pending() once more after
     // the last step

@@ -99,7 +99,7 @@ __device__ __forceinline__ void stage_world(WT* dst, const DevWorld* __restrict_
         dst->radius = src->radius; dst->half_height = src->half_height; dst->lower_off = src->lower_off;
         dst->dt = src->dt; dst->inv_dt = src->inv_dt; dst->erp_inv_dt = src->erp_inv_dt; dst->cfm_factor = src->cfm_factor;
         dst->prediction = src->prediction; dst->allowed_linear_error = src->allowed_linear_error; dst->aabb_margin = src->aabb_margin;
-        dst->scale = src->scale;
+        dst->scale = src->scale; dst->win_q = src->win_q;
         dst->grid_n = WT::kGrid > 1 ? src->grid_n : 0; dst->grid_x0 = src->grid_x0; dst->grid_inv_w = src->grid_inv_w;
     }
     if (WT::kGrid > 1)
@@ -318,6 +318,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     Contacts<> ct;
     env_init(W, e);
     Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
+    // running minimum of the SQUARED physics-space distance to the goals (Stepper::finish_step_sq):
+    // one sqrt and one division at the end of the rollout instead of one per step
     float score = __int_as_float(0x7f800000);
     int win_step = -1, steps = 0;
     const uint8_t* genome = genomes + i * (int64_t)genome_len;
@@ -419,10 +421,10 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
         const bool in_genes = t < main_steps;
         const int need = run ? sim.begin_step(in_genes ? gene : 0u) : 0;
         solve_in_rounds<Sim>(run, need, [&](int entry, int stride) {
-            float d = sim.finish_step(entry, stride);
+            const float q = sim.finish_step_sq(entry, stride);
             ++steps;
             ++t;
-            score = fminf(score, d);
+            score = fminf(score, q);
             bool won = (e.flags & FLAG_WON) != 0;
             if (won && win_step < 0) win_step = steps;
             if (in_genes && ++rep == repeat_move) {
@@ -441,6 +443,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     if (!live) return;
     if (e.flags & FLAG_OVERFLOW) atomicOr(overflow, 1);  // more live manifolds than PRL_MAX_CONTACTS: reported by prl_batch_sync
     env_store(W, e, ct, st, n, i);
+    score = sqrtf(score) / W.scale;  // distance_to_goals (common.rs:192) of the closest approach, editor pixels
     st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
     st[(int64_t)F_WIN_STEP * n + i] = (uint32_t)win_step;
     st[(int64_t)F_STEPS * n + i] = (uint32_t)steps;

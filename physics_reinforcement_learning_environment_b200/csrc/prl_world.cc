@@ -72,6 +72,18 @@ int build_dev_world(prl_world* w) {
     d.allowed_linear_error = 0.001f;
     d.aabb_margin = d.prediction / 2.0f;
     d.scale = kScale;
+    {
+        // largest f32 q with sqrtf(q) / scale < 1e-7f (Environment::step's win threshold, common.rs:335):
+        // both operations are correctly rounded and monotone in q, so bisect on the bit pattern
+        uint32_t lo = 0u, hi = 0x7f800000u;  // q = 0 passes, +inf does not
+        while (hi - lo > 1u) {
+            uint32_t mid = lo + (hi - lo) / 2u;
+            float q;
+            memcpy(&q, &mid, 4);
+            if (sqrtf(q) / d.scale < 1e-7f) lo = mid; else hi = mid;
+        }
+        memcpy(&d.win_q, &lo, 4);
+    }
 
     // Environment::new (common.rs:70-86): rotation-locked dynamic body + capsule_y collider
     d.half_height = 0.5f * kPlayerDepth * kScale;

@@ -36,6 +36,9 @@ struct alignas(16) DevWorldT {
     // integration parameters (rapier IntegrationParameters::default, derived values)
     float dt, inv_dt, erp_inv_dt, cfm_factor, prediction, allowed_linear_error, aabb_margin;
     float scale;  // BEVY_TO_PHYSICS_SCALE (distance_to_goals divides by it, common.rs:192)
+    // the win test of common.rs:335 on the SQUARED physics-space distance q: sqrt(q) / scale < 1e-7
+    // iff q <= win_q (sqrt and the division are monotone; the host finds the largest such q bit by bit)
+    float win_q;
     // colliders in insertion order; 0 = player capsule (common.rs:86, 125, 140-144)
     float cx[MC], cy[MC], cc[MC], cs[MC];  // pose (initial pose for pushable blocks)
     float hx[MC], hy[MC];                  // cuboid half extents

@@ -58,7 +58,7 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
     using Sim = Stepper<NB, MAXC, WT, PR>;
     alignas(16) static unsigned char pool[Sim::kWarpBytes + Sim::kPoolPad];
     Sim sim(W, e, k, pool);
-    float score = INFINITY;
+    float qmin = INFINITY;
     int win = -1, steps = 0;
     auto record = [&]() {
         if (!traj) return;
@@ -71,24 +71,23 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
     bool stop = false;
     for (int g = 0; g < genome_len && !stop; ++g) {
         for (int r = 0; r < repeat_move; ++r) {
-            float d = sim.step(genome[g] & 7u);
+            // the rollout kernel's path: running minimum of the squared distance, one sqrt at the end
+            qmin = fminf(qmin, sim.step_q(genome[g] & 7u));
             count_need(sim);
             ++steps;
             if (traj) sim.detect_pending();  // what a kernel does before it stores the state
             record();
-            score = fminf(score, d);
             bool won = (e.flags & FLAG_WON) != 0;
             if (won && win < 0) win = steps;
             if (won && early_exit) { stop = true; break; }
         }
     }
     for (int r = 0; r < number_of_steps % repeat_move; ++r) {
-        float d = sim.step(0u);
+        qmin = fminf(qmin, sim.step_q(0u));
         count_need(sim);
         ++steps;
         if (traj) sim.detect_pending();
         record();
-        score = fminf(score, d);
         bool won = (e.flags & FLAG_WON) != 0;
         if (won && win < 0) win = steps;
         if (won && early_exit) break;
@@ -97,7 +96,7 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
     *win_out = win;
     *steps_out = steps;
     *overflow = (e.flags & FLAG_OVERFLOW) ? 1 : 0;
-    return score;
+    return sqrtf(qmin) / W.scale;
 }
 
 // the policy rollout of prl_kernels.cuh policy_rollout_kernel for one environment (theta: this
@@ -144,7 +143,7 @@ static void copy_world(WT& d, const DevWorld& s) {
     d.n_player_pairs = s.n_player_pairs; d.n_slots = s.n_slots; d.two_body_pairs = s.two_body_pairs;
     d.radius = s.radius; d.half_height = s.half_height; d.lower_off = s.lower_off;
     d.dt = s.dt; d.inv_dt = s.inv_dt; d.erp_inv_dt = s.erp_inv_dt; d.cfm_factor = s.cfm_factor;
-    d.prediction = s.prediction; d.allowed_linear_error = s.allowed_linear_error; d.aabb_margin = s.aabb_margin; d.scale = s.scale;
+    d.prediction = s.prediction; d.allowed_linear_error = s.allowed_linear_error; d.aabb_margin = s.aabb_margin; d.scale = s.scale; d.win_q = s.win_q;
     d.grid_n = WT::kGrid > 1 ? s.grid_n : 0; d.grid_x0 = s.grid_x0; d.grid_inv_w = s.grid_inv_w;
     if (WT::kGrid > 1) for (int c = 0; c < WT::kGrid; ++c) for (int q = 0; q < 4; ++q) d.grid_mask[c][q] = s.grid_mask[c][q];
     for (int c = 0; c < s.n_colliders; ++c) {
