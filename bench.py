@@ -288,7 +288,7 @@ def main():
             except Exception:
                 traffic, issue = None, None
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world_size == 1:  # the CPU leg is timed on rank 0 at N = 1 only
             cores = os.cpu_count() or 1
             # bounded sample: ~cpu-seconds of host work at ~3 us per env-step per core
             sample_envs = int(max(cores, min(args.envs, args.cpu_seconds * cores / (3.0e-6 * args.horizon))))

@@ -186,6 +186,9 @@ void prl_batch_destroy(prl_batch* b) {
     if (b->overflow) cudaFree(b->overflow);
     if (b->stage) cudaFree(b->stage);
     if (b->stage2) cudaFree(b->stage2);
+    if (b->traj) cudaFree(b->traj);
+    if (b->pinned) cudaFreeHost(b->pinned);
+    if (b->pinned_free) cudaEventDestroy(b->pinned_free);
     delete b;
 }
 
@@ -216,11 +219,20 @@ int prl_batch_step(prl_batch* b, const uint8_t* moves) {
     DeviceGuard g(b->device);
     const uint8_t* dm = moves;
     if (!is_device_ptr(moves)) {
+        // host moves: through a pinned buffer owned by the batch, so that the transfer is asynchronous
+        // and the call does not wait for the stream (a closed loop on the host steps once per call)
         int rc = ensure_stage(&b->stage, &b->stage_bytes, (size_t)b->n);
         if (rc != PRL_OK) return rc;
-        CUDA_TRY(cudaMemcpyAsync(b->stage, moves, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
-        // the caller may reuse `moves` as soon as we return
-        CUDA_TRY(cudaStreamSynchronize(b->stream));
+        if (b->pinned_bytes < (size_t)b->n) {
+            if (b->pinned) { CUDA_TRY(cudaStreamSynchronize(b->stream)); cudaFreeHost(b->pinned); b->pinned = nullptr; b->pinned_bytes = 0; }
+            CUDA_TRY(cudaMallocHost(&b->pinned, (size_t)b->n));
+            b->pinned_bytes = (size_t)b->n;
+        }
+        if (!b->pinned_free) CUDA_TRY(cudaEventCreateWithFlags(&b->pinned_free, cudaEventDisableTiming));
+        else CUDA_TRY(cudaEventSynchronize(b->pinned_free));  // the previous step's transfer has left the buffer
+        memcpy(b->pinned, moves, (size_t)b->n);
+        CUDA_TRY(cudaMemcpyAsync(b->stage, b->pinned, (size_t)b->n, cudaMemcpyHostToDevice, b->stream));
+        CUDA_TRY(cudaEventRecord(b->pinned_free, b->stream));
         dm = (const uint8_t*)b->stage;
     }
     return launch_step(b, dm, 0, 1);
@@ -445,9 +457,11 @@ int prl_batch_trajectory(prl_batch* b, int64_t n, const uint8_t* genomes, int32_
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t off_s = up(g_host ? gbytes : 0), off_d = off_s + up(s_host ? state_bytes : 0), off_w = off_d + up(d_host ? dist_bytes : 0);
     const size_t total = off_w + up(w_host ? won_bytes : 0);
-    unsigned char* scratch = nullptr;
-    if (total > 0) CUDA_TRY(cudaMalloc((void**)&scratch, total));
-    struct Free { unsigned char* p; ~Free() { if (p) cudaFree(p); } } guard{scratch};
+    if (total > 0) {
+        int rc = ensure_stage(&b->traj, &b->traj_bytes, total);
+        if (rc != PRL_OK) return rc;
+    }
+    unsigned char* scratch = (unsigned char*)b->traj;
     const uint8_t* dg = genomes;
     if (g_host) { CUDA_TRY(cudaMemcpyAsync(scratch, genomes, gbytes, cudaMemcpyHostToDevice, b->stream)); dg = scratch; }
     float* ds = s_host ? (float*)(scratch + off_s) : out_state;

@@ -30,6 +30,14 @@ struct prl_batch {
     size_t stage_bytes = 0;
     void* stage2 = nullptr;
     size_t stage2_bytes = 0;
+    // pinned host buffer for the per-step moves of a closed loop on the host: the caller's array is
+    // copied here and the transfer is asynchronous, so prl_batch_step does not wait for the stream
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaEvent_t pinned_free = nullptr;  // the last transfer out of `pinned` has completed
+    // scratch of prl_batch_trajectory (kept between calls)
+    void* traj = nullptr;
+    size_t traj_bytes = 0;
     int64_t launches = 0;
 };
 

@@ -650,25 +650,25 @@ struct Stepper {
         int ns = 0;
         float px[2] = {0.0f, 0.0f}, py[2] = {0.0f, 0.0f}, pd[2] = {0.0f, 0.0f};
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            if (k < m.npts && m.dist[k] < W.prediction) {
-                v2 wp = xform(pose1, m.p1[k]);
-                v2 half = normal * m.dist[k];
+        for (int i = 0; i < 2; ++i) {
+            if (i < m.npts && m.dist[i] < W.prediction) {
+                v2 wp = xform(pose1, m.p1[i]);
+                v2 half = normal * m.dist[i];
                 float qx = wp.x + half.x / 2.0f, qy = wp.y + half.y / 2.0f;
-                if (ns == 0) { px[0] = qx; py[0] = qy; pd[0] = m.dist[k]; }
-                else { px[1] = qx; py[1] = qy; pd[1] = m.dist[k]; }
+                if (ns == 0) { px[0] = qx; py[0] = qy; pd[0] = m.dist[i]; }
+                else { px[1] = qx; py[1] = qy; pd[1] = m.dist[i]; }
                 ++ns;
             }
         }
         if (scan && gs_n >= 0) {  // a player pair: floor contacts among its solver contacts (common.rs:234-238)
             const int body = info_b2(W.pair_info[pair]);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (k < ns) {
-                    float qy = (py[k] - (e.y[0] - W.lower_off)) / W.radius;
+            for (int i = 0; i < 2; ++i) {
+                if (i < ns) {
+                    float qy = (py[i] - (e.y[0] - W.lower_off)) / W.radius;
                     if (qy < -0.707f) {
-                        if (gs_n == 0) { gs_x[0] = px[k]; gs_y[0] = py[k]; gs_b[0] = body; }
-                        else if (gs_n == 1) { gs_x[1] = px[k]; gs_y[1] = py[k]; gs_b[1] = body; }
+                        if (gs_n == 0) { gs_x[0] = px[i]; gs_y[0] = py[i]; gs_b[0] = body; }
+                        else if (gs_n == 1) { gs_x[1] = px[i]; gs_y[1] = py[i]; gs_b[1] = body; }
                         ++gs_n;
                     }
                 }
@@ -1163,8 +1163,7 @@ struct Stepper {
             ntb = popcount(cm_tb) + popcount(cm_tb & e.ns2);
             nplayer = popcount(pl) + popcount(pl & e.ns2);
             need = popcount(sel_) + popcount(sel_ & e.ns2);
-            return;
-        }
+        } else {
 #pragma unroll 1
         for (int pass = NB == 1 ? 1 : 0; pass < 2; ++pass) {
 #pragma unroll 1
@@ -1186,6 +1185,7 @@ struct Stepper {
                 if (two_body) ntb += ns;
                 else if (p < W.n_player_pairs) nplayer += ns;
             }
+        }
         }
     }
 
@@ -1554,15 +1554,17 @@ struct Stepper {
         return nfc;
     }
     PRL_D bool touches_pushable_block() const {
-        if (NB == 1) return false;
+        bool touching = false;
+        if (NB > 1) {
 #pragma unroll 1
-        for (int it = it_begin(); it_ok(it); it = it_next(it)) {
-            const int slot = it_slot(it);
-            const int p = pair_of(slot);
-            if (p >= W.n_player_pairs) break;
-            if (ns_of(slot) > 0 && info_b2(W.pair_info[p]) >= 0) return true;
+            for (int it = it_begin(); it_ok(it) && !touching; it = it_next(it)) {
+                const int slot = it_slot(it);
+                const int p = pair_of(slot);
+                if (p >= W.n_player_pairs) break;
+                touching = ns_of(slot) > 0 && info_b2(W.pair_info[p]) >= 0;
+            }
         }
-        return false;
+        return touching;
     }
     PRL_D void observe(float* obs) const {
         const int nb = W.n_bodies;

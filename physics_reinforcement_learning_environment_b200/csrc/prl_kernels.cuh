@@ -216,8 +216,8 @@ __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, const C
         }
     }
     int base = F_DYN + 8 * (W.n_bodies - 1);
-#pragma unroll 1
     uint32_t left = e.used;
+#pragma unroll 1
     for (int k = 0; k < count; ++k) {
         int slot = direct ? __ffs((int)left) - 1 : (int)((e.order >> (4 * k)) & 15u);
         left &= left - 1;
