@@ -2,6 +2,7 @@
 // entry point needs a CUDA device and fails with PRL_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -347,6 +348,15 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
         // warp per block, so that it spreads over twice as many SMs: such a rollout is bound by the
         // latency of a single warp's step, not by throughput
         const bool tiny = (b->n + kBlock - 1) / kBlock < (int64_t)b->sm_count;
+        // ... in sparse warps: as many environments per warp as give every SM 16 warps (single-body
+        // worlds) or 4 (with pushable blocks: their row storage is 13.5 KB of shared memory per warp).
+        // Measured on one B200, 1000 steps: jump.json 4096 environments 7.5e8 env-steps/s in dense warps,
+        // 9.6e8 / 9.9e8 / 1.03e9 with 4 / 8 / 16 warps per SM; push.json 4096: 2.6e8 dense, 3.0e8 with 4,
+        // 1.6e8 with 16. One environment alone in a warp steps in 3.06 us on jump.json: the floor.
+        static const int warps_env = [] { const char* v = getenv("PRL_TINY_WARPS_PER_SM"); int k = v ? atoi(v) : 0; return k; }();
+        const int warps_per_sm = warps_env > 0 ? warps_env : (b->host_world.n_bodies == 1 ? 16 : 4);
+        int64_t sparse = (b->n + (int64_t)warps_per_sm * b->sm_count - 1) / ((int64_t)warps_per_sm * b->sm_count);
+        const int sparse_lanes = (int)(sparse < 1 ? 1 : (sparse > 32 ? 32 : sparse));
         cudaError_t le = cudaSuccess;
 #define PRL_ROLLOUT(NB_, WT_, BLOCK_)                                                                                     \
     do {                                                                                                                  \
@@ -357,9 +367,10 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
             le = cudaFuncSetAttribute(rollout_kernel<NB_, WT_, BLOCK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
             if (le == cudaSuccess) configured |= dev_bit;                                                                 \
         }                                                                                                                 \
+        const int per_block = BLOCK_ == kWarpBlock ? sparse_lanes : BLOCK_;                                               \
         if (le == cudaSuccess)                                                                                            \
-            rollout_kernel<NB_, WT_, BLOCK_><<<(unsigned)((b->n + BLOCK_ - 1) / BLOCK_), BLOCK_, smem, b->stream>>>(      \
-                b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw, b->overflow); \
+            rollout_kernel<NB_, WT_, BLOCK_><<<(unsigned)((b->n + per_block - 1) / per_block), BLOCK_, smem, b->stream>>>( \
+                b->dev_world, b->state, b->n, dg, genome_len, repeat_move, number_of_steps, early_exit, ds, dw, b->overflow, sparse_lanes); \
     } while (0)
         switch (pick_variant(b->host_world)) {
             case V1_SMALL: if (tiny) PRL_ROLLOUT(1, DevWorldSmall, kWarpBlock); else PRL_ROLLOUT(1, DevWorldSmall, kBlock); break;

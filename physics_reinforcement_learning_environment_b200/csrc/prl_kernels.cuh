@@ -305,15 +305,19 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
                                                          const uint8_t* __restrict__ genomes, int genome_len, int repeat_move,
                                                          int number_of_steps, int early_exit,
                                                          float* __restrict__ out_score, int32_t* __restrict__ out_win,
-                                                         int* __restrict__ overflow) {
+                                                         int* __restrict__ overflow, int lanes) {
     using Sim = SimOf<NB, WT, BLOCK>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WT& W = *reinterpret_cast<WT*>(smem_raw);
     unsigned char* row_pool = smem_raw + ((sizeof(WT) + 15) / 16) * 16;
     stage_world(&W, dw);
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i < n;  // see step_kernel
-    if (!live) i = n - 1;
+    // `lanes` environments per warp. Populations too small to fill the GPU (BLOCK == kWarpBlock) run in
+    // SPARSE warps: a rollout of few environments is bound by the latency of a warp's step, and a warp
+    // executes the union of its lanes' paths -- with 7 environments instead of 32 most steps of a random
+    // population are pure free flight, and four such warps per SM overlap their latencies.
+    int64_t i = BLOCK == kWarpBlock ? (int64_t)blockIdx.x * lanes + threadIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i < n && (BLOCK != kWarpBlock || (int)threadIdx.x < lanes);
+    if (!live) i = n - 1;  // pad lanes only take part in the warp's votes and the block's barriers
     Env<NB> e;
     Contacts<> ct;
     env_init(W, e);
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     // warps in the same phase of the step (shared instruction fetches).
     const int main_steps = genome_len * repeat_move;
     const int total = main_steps + number_of_steps % repeat_move;
-    int g = 0, rep = 0, t = 0, iter = 0;
+    int g = 0, rep = 0, t = live ? 0 : total, iter = 0;
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
     int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes + Sim::kPoolPad);  // only if BLOCK == kBigBlock
 #if defined(PRL_PHASE_TIMING)
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
             win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
             steps = (int)st[(int64_t)F_STEPS * n + i];
-            t = (int)st[(int64_t)F_ROLL * n + i];
+            t = live ? (int)st[(int64_t)F_ROLL * n + i] : total;
             sim.refresh_solver_contacts();
             genome = genomes + i * (int64_t)genome_len;
             g = t < main_steps ? t / repeat_move : genome_len;
