@@ -339,10 +339,9 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
     int32_t* dw = win_host ? nullptr : out_step_of_win;
     {
         // one 448-thread block per SM once the batch can fill half the SMs that way, else 64-thread
-        // blocks. Only the kernels with pushable blocks gain (their step is twice the code). Single-body
-        // kernels measured 10-13 % slower in lock step, and 1.5 % slower with SM-wide blocks that only
-        // meet to regroup (round 2: sorting the few walking players of a random population into their
-        // own warps does not shorten those warps' dependent chain, which is what bounds the kernel).
+        // blocks: the SM's warps then run in lock step (one barrier per step) and share their instruction
+        // fetches -- the step's code is larger than the SM's 32 KB instruction cache
+        // (profiles/r02_icache_probe.txt). Kernels with pushable blocks are also regrouped every 128 steps.
         const bool big = b->n >= (int64_t)b->sm_count * kBigBlock / 2;
         // a population too small to give every SM a 64-thread block (config C2: 4096 agents) runs one
         // warp per block, so that it spreads over twice as many SMs: such a rollout is bound by the
@@ -380,7 +379,14 @@ int prl_batch_rollout(prl_batch* b, const uint8_t* genomes, int32_t genome_len, 
                 else PRL_ROLLOUT(2, DevWorldSmall, kBlock);
                 break;
             case VN_SMALL: if (big) PRL_ROLLOUT(MIDB, DevWorldSmall, kBigBlock); else PRL_ROLLOUT(MIDB, DevWorldSmall, kBlock); break;
-            case V1_BIG: if (tiny) PRL_ROLLOUT(1, DevWorld, kWarpBlock); else PRL_ROLLOUT(1, DevWorld, kBlock); break;
+            // large single-body worlds (general tables, x grid: the largest single-body step): SM-wide blocks
+            // in lock step, +6.5 % on the synthetic 64-obstacle world (5.79e9 -> 6.17e9); the compact
+            // single-body kernel loses 9 % that way on jump.json and stays in 64-thread blocks
+            case V1_BIG:
+                if (big) PRL_ROLLOUT(1, DevWorld, kBigBlock);
+                else if (tiny) PRL_ROLLOUT(1, DevWorld, kWarpBlock);
+                else PRL_ROLLOUT(1, DevWorld, kBlock);
+                break;
             case VN_BIG: if (big) PRL_ROLLOUT(MIDB, DevWorld, kBigBlock); else PRL_ROLLOUT(MIDB, DevWorld, kBlock); break;
             default: PRL_ROLLOUT(MAXB, DevWorld, kBlock); break;
         }

@@ -383,7 +383,9 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             if (p0 + p1 + p2 + p3 == -12345.0f) score = p0;
         }
 #endif
-        if (BLOCK == kBigBlock && PRL_UNLIKELY(iter > 0 && iter % kRegroupEvery == 0)) {
+        // (single-body worlds in SM-wide blocks run in lock step but are not regrouped: sorting the few
+        // walking players of a population into their own warps does not shorten those warps' chains)
+        if (BLOCK == kBigBlock && NB > 1 && PRL_UNLIKELY(iter > 0 && iter % kRegroupEvery == 0)) {
             // ---- regroup: park, sort, pick up (all threads of the block are here, nothing pending)
             int* hist = regroup;
             int* perm_env = regroup + kRegroupKeys;
