@@ -69,6 +69,10 @@ typedef struct prl_ga prl_ga;
 
 const char* prl_last_error(void);
 int32_t prl_abi_version(void);
+/* Debug builds only (libprl_debug.so, -DPRL_BOUNDS_CHECK: every run-time index of the kernels is
+ * checked): bit mask of the checks that failed on the current device since the library was loaded,
+ * 0 = none; -1 = this library was built without the checks (the product); -2 = CUDA failure. */
+int32_t prl_debug_bounds_violations(void);
 /* number of CUDA devices visible to the library (0 when none / no driver) */
 int32_t prl_device_count(void);
 

@@ -45,6 +45,7 @@ _SIGNATURES = {
     "prl_last_error": (C.c_char_p, []),
     "prl_abi_version": (C.c_int32, []),
     "prl_device_count": (C.c_int32, []),
+    "prl_debug_bounds_violations": (C.c_int32, []),
     "prl_world_create": (C.c_int, [C.POINTER(C.c_float), C.POINTER(PrlObject), C.c_int32, C.POINTER(C.c_void_p)]),
     "prl_world_from_json": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "prl_world_to_json": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),

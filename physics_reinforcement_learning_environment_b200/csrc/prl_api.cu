@@ -68,6 +68,16 @@ extern "C" {
 
 const char* prl_last_error(void) { return prl::last_error(); }
 int32_t prl_abi_version(void) { return PRL_ABI_VERSION; }
+int32_t prl_debug_bounds_violations(void) {
+#if defined(PRL_BOUNDS_CHECK)
+    unsigned int v = 0;
+    if (cudaDeviceSynchronize() != cudaSuccess) return -2;
+    if (cudaMemcpyFromSymbol(&v, g_prl_bounds_violations, sizeof v) != cudaSuccess) return -2;
+    return (int32_t)v;
+#else
+    return -1;
+#endif
+}
 int32_t prl_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

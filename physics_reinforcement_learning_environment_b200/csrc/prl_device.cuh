@@ -57,6 +57,21 @@
 #define PRL_TRACE(stmt) do { } while (0)
 #endif
 
+// PRL_BOUNDS_CHECK (libprl_debug.so, run by tests/test_bounds_gpu.py; never the product build): every
+// run-time index into the row planes, the manifold records, the world tables, the state arrays and the
+// genomes is checked, and a failed check sets bit `code` of a device word that
+// prl_debug_bounds_violations() reads back. compute-sanitizer is not available on the GPU pool.
+#if defined(PRL_BOUNDS_CHECK) && defined(__CUDACC__)
+__device__ unsigned int g_prl_bounds_violations;
+#endif
+#if defined(PRL_BOUNDS_CHECK) && defined(__CUDA_ARCH__)
+#define PRL_CHECK(cond, code) do { if (!(cond)) atomicOr(&g_prl_bounds_violations, 1u << (code)); } while (0)
+#else
+#define PRL_CHECK(cond, code) do { } while (0)
+#endif
+// codes: 0 row entry read, 1 row entry written, 2 manifold slot, 3 candidate pair, 4 state slot in HBM,
+//        5 gene, 6 regroup table, 7 body
+
 namespace prl {
 
 PRL_D int first_zero_bit(uint32_t used) {  // index of the lowest clear bit, 32 if none
@@ -580,12 +595,13 @@ struct Stepper {
     // lie up to 32 entries past a plane (it is never used), so a block's planes are followed by kPoolPad bytes.
     static constexpr int kPoolPad = 256;
     PRL_D int row_entry(int j) const { return ent0 + j * stride; }
-    PRL_D f4& q0(int en) const { return reinterpret_cast<f4*>(pool)[en]; }
-    PRL_D f4& q1(int en) const { return reinterpret_cast<f4*>(pool + kOff1)[en]; }
-    PRL_D f2& q2(int en) const { return reinterpret_cast<f2*>(pool + kOff2)[en]; }
-    PRL_D float& acc_n(int en) const { return reinterpret_cast<float*>(pool + kOff3)[en]; }
-    PRL_D float& acc_t(int en) const { return reinterpret_cast<float*>(pool + kOff4)[en]; }
-    PRL_D f2& q5(int en) const { return reinterpret_cast<f2*>(pool + kOff5)[en]; }
+    // (reads may run one row -- 32 entries -- past a plane: the sweeps fetch one row ahead, kPoolPad)
+    PRL_D f4& q0(int en) const { PRL_CHECK(en >= 0 && en < kEntries + 32, 0); return reinterpret_cast<f4*>(pool)[en]; }
+    PRL_D f4& q1(int en) const { PRL_CHECK(en >= 0 && en < kEntries + 32, 0); return reinterpret_cast<f4*>(pool + kOff1)[en]; }
+    PRL_D f2& q2(int en) const { PRL_CHECK(en >= 0 && en < kEntries + 32, 0); return reinterpret_cast<f2*>(pool + kOff2)[en]; }
+    PRL_D float& acc_n(int en) const { PRL_CHECK(en >= 0 && en < kEntries + 32, 0); return reinterpret_cast<float*>(pool + kOff3)[en]; }
+    PRL_D float& acc_t(int en) const { PRL_CHECK(en >= 0 && en < kEntries + 32, 0); return reinterpret_cast<float*>(pool + kOff4)[en]; }
+    PRL_D f2& q5(int en) const { PRL_CHECK(en >= 0 && en < kEntries + 32, 0); return reinterpret_cast<f2*>(pool + kOff5)[en]; }
 
     // slot == pair index for worlds with at most S candidate pairs (the shipped levels): the live
     // manifolds are a bit mask, and selection / broad phase are mask algebra
@@ -617,7 +633,7 @@ struct Stepper {
     PRL_D static int info_c1(uint32_t info) { return (int)(info & 0xffu); }
     PRL_D static int info_c2(uint32_t info) { return (int)((info >> 8) & 0xffu); }
     PRL_D int pair_at(int k) const { return pair_of(slot_at(k)); }
-    PRL_D Iso body_pose(int b) const { Iso p; p.t = V(sel(e.x, b), sel(e.y, b)); p.c = sel(e.c, b); p.s = sel(e.s, b); return p; }
+    PRL_D Iso body_pose(int b) const { PRL_CHECK(b >= 0 && b < NB, 7); Iso p; p.t = V(sel(e.x, b), sel(e.y, b)); p.c = sel(e.c, b); p.s = sel(e.s, b); return p; }
     PRL_D Iso collider_pose(int c) const {
         int b = W.body_of[c];
         if (b >= 0) return body_pose(b);
@@ -634,6 +650,7 @@ struct Stepper {
     PRL_D void wake_strong(int b) { e.sleeping &= ~(1u << b); put(e.timer, b, 0.0f); }
 
     PRL_D void load_manifold(int slot, Manifold& m) const {
+        PRL_CHECK(slot >= 0 && slot < S, 2);
         f4 a = k.mf[slot][0], b = k.mf[slot][1], c = k.mf[slot][2], d = k.mf[slot][3];
         m.npts = (int)((f32_bits(a.x) >> 8) & 0xfu);
         m.n1 = V(a.y, a.z); m.n2 = V(a.w, b.x);
@@ -646,6 +663,8 @@ struct Stepper {
     // scan: the pair is one of the player's -- its floor contacts feed the ground-contact scan
     template <bool SCAN = false>
     PRL_D void store_manifold(int slot, int pair, const Manifold& m, const Iso& pose1, bool scan = SCAN) {
+        PRL_CHECK(slot >= 0 && slot < S, 2);
+        PRL_CHECK(pair >= 0 && pair < W.n_pairs, 3);
         v2 normal = rot(pose1.c, pose1.s, m.n1);
         int ns = 0;
         float px[2] = {0.0f, 0.0f}, py[2] = {0.0f, 0.0f}, pd[2] = {0.0f, 0.0f};
@@ -910,6 +929,8 @@ struct Stepper {
     // angular response), which evaluates to the same values as rapier's ground formulas.
     PRL_D int generate_constraint(int slot, int nrows, const f4& s0, const f4& s1) {
         int p = pair_of(slot), ns = ns_of(slot);
+        PRL_CHECK(slot >= 0 && slot < S, 2);
+        PRL_CHECK(p >= 0 && p < W.n_pairs, 3);
         const uint32_t info = W.pair_info[p];
         int h1 = info_b1(info), h2 = info_b2(info);
         bool two_body = h1 >= 0 && h2 >= 0;
@@ -975,6 +996,7 @@ struct Stepper {
             r2.x = dot(dv, tan1); r2.y = inv0(tr);
             int j = nrows + k;
             int en = row_entry(j);
+            PRL_CHECK(en >= 0 && en < kEntries, 1);
             q0(en) = r0; q1(en) = r1; q2(en) = r2;
             acc_n(en) = 0.0f; acc_t(en) = 0.0f;
             if (NB > 2) {
@@ -1022,6 +1044,7 @@ struct Stepper {
         float a2 = BODY >= 0 ? da[B] : sel(da, b2);
         float dvel = -dot(dir, l2) + g2 * a2 + rhs;
         float ni = row_cfm(r.b.w) * fmaxf(acc - rr * dvel, 0.0f);
+        PRL_CHECK(en >= 0 && en < kEntries, 1);
         acc_n(en) = ni;
         float dl = ni - acc;
         l2 = l2 + (dir * im2) * -dl;
@@ -1041,6 +1064,7 @@ struct Stepper {
         float dvel = -dot(dir, l2) + g2 * a2 + rhs;
         float limit = kFriction * r.accn;
         float ni = fminf(fmaxf(acc - rr * dvel, -limit), limit);
+        PRL_CHECK(en >= 0 && en < kEntries, 1);
         acc_t(en) = ni;
         float dl = ni - acc;
         l2 = l2 + (dir * im2) * -dl;
@@ -1088,6 +1112,7 @@ struct Stepper {
     template <bool NORMAL>
     PRL_D void two_body_row(int j, float (&dlx)[NB], float (&dly)[NB], float (&da)[NB]) {
         const int en = row_entry(j);
+        PRL_CHECK(en >= 0 && en < kEntries, 1);
         const f4 r0 = q0(en);
         v2 dir = V(r0.x, r0.y);
         uint32_t bodies = 0;
@@ -1132,6 +1157,7 @@ struct Stepper {
         int en = row_entry(0);
 #pragma unroll 1
         for (int j = 0; j < nrows; ++j, en += stride) {
+            PRL_CHECK(en >= 0 && en < kEntries, 1);
             f4 r = q1(en);
             r.x = r.z;
             r.w = NB <= 2 ? 1.0f : bits_f32(f32_bits(r.w) | (1u << 16));
@@ -1377,6 +1403,7 @@ struct Stepper {
             for (uint32_t m_ = cand; m_ != 0; m_ &= m_ - 1) {
                 PRL_TRACE(++tr_cand);
                 const int p = first_bit_from(m_, 0);
+                PRL_CHECK(p < W.n_pairs && p < S, 3);
                 const uint32_t info = W.pair_info[p];
                 const f4 he = *reinterpret_cast<const f4*>(W.pair_he[p]);
                 Manifold m;

@@ -182,12 +182,14 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct
     // this loop is a chain of global-memory latencies, not of bytes
 #pragma unroll 1
     for (int k = 0; k < count; ++k) {
+        PRL_CHECK(k < W.n_slots, 4);
         int f = base + MF_WORDS * k;
         uint32_t w[MF_WORDS];
 #pragma unroll
         for (int j = 0; j < MF_WORDS; ++j) w[j] = st[(int64_t)(f + j) * n + i];
         const uint32_t h = w[0];
         int slot = direct ? (int)(h & 0xffu) : k;
+        PRL_CHECK(slot >= 0 && slot < MAXC, 2);
         if (direct) e.used |= 1u << slot;
         f4* rec = ct.mf[slot];
         f4 q;
@@ -220,6 +222,7 @@ __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, const C
 #pragma unroll 1
     for (int k = 0; k < count; ++k) {
         int slot = direct ? __ffs((int)left) - 1 : (int)((e.order >> (4 * k)) & 15u);
+        PRL_CHECK(k < W.n_slots && slot >= 0 && slot < MAXC, 4);
         left &= left - 1;
         int f = base + MF_WORDS * k;
         const f4* rec = ct.mf[slot];
@@ -404,6 +407,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             __syncthreads();
             int off = 0;
             for (int k = key + 1; k < kRegroupKeys; ++k) off += hist[k];
+            PRL_CHECK(off + pos >= 0 && off + pos < kBigBlock && key >= 0 && key < kRegroupKeys, 6);
             perm_env[off + pos] = (int)(i - (int64_t)blockIdx.x * BLOCK);
             perm_live[off + pos] = live ? 1 : 0;
             __syncthreads();
@@ -436,6 +440,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             if (in_genes && ++rep == repeat_move) {
                 rep = 0;
                 if (++g < genome_len) gene = genome[g] & 7u;
+                PRL_CHECK(g <= genome_len && i >= 0 && i < n, 5);
             }
             if (won && early_exit) t = in_genes ? main_steps : total;
         });

@@ -65,6 +65,7 @@ extern "C" {
     pub fn prl_last_error() -> *const c_char;
     pub fn prl_abi_version() -> i32;
     pub fn prl_device_count() -> i32;
+    pub fn prl_debug_bounds_violations() -> i32;
 
     pub fn prl_world_create(player_position: *const f32, objs: *const prl_object, n_objects: i32, out: *mut *mut prl_world) -> c_int;
     pub fn prl_world_from_json(utf8: *const c_char, len: usize, out: *mut *mut prl_world) -> c_int;
