@@ -40,7 +40,7 @@ typedef enum {
     PRL_ERR_CAPACITY = -3,  /* world exceeds the compiled limits (see prl_limits) */
     PRL_ERR_NO_GOAL = -4,   /* distance_to_goals() on a goal-less world (reference: None / unwrap panic) */
     PRL_ERR_CUDA = -5,      /* CUDA runtime failure, or no usable device */
-    PRL_ERR_OVERFLOW = -6   /* an environment needed more simultaneous contact manifolds than PRL_MAX_CONTACTS */
+    PRL_ERR_OVERFLOW = -6   /* an environment needed more simultaneous contact manifolds than the kernels hold (PRL_MAX_CONTACTS) */
 } prl_status;
 
 #define PRL_MOVE_LEFT 1u
@@ -52,7 +52,9 @@ typedef enum {
 #define PRL_MAX_BLOCKS 128    /* fixed + pushable blocks per world */
 #define PRL_MAX_PAIRS 128     /* candidate collider pairs per world */
 #define PRL_MAX_GOALS 16
-#define PRL_MAX_CONTACTS 16   /* simultaneous manifolds with solver contacts per environment */
+#define PRL_MAX_CONTACTS 16   /* simultaneous contact manifolds per environment in worlds with more candidate pairs
+                                 than that (smaller worlds have a slot per pair and no limit); twice as many,
+                                 32, when such a world has pushable blocks */
 
 /* One `ObjectAndTransform` (common.rs:26-31). kind: 0 = WorldObject::Block{fixed:true},
  * 1 = Block{fixed:false}, 2 = Goal (common.rs:46-49). */

@@ -68,9 +68,14 @@ extern "C" {
 
 const char* prl_last_error(void) { return prl::last_error(); }
 int32_t prl_abi_version(void) { return PRL_ABI_VERSION; }
+#if defined(PRL_BOUNDS_CHECK)
+// negative control of the checking machinery: a check that must fail (code 30)
+__global__ void bounds_selftest_kernel(int n) { PRL_CHECK((int)threadIdx.x >= n, 30); }
+#endif
 int32_t prl_debug_bounds_violations(void) {
 #if defined(PRL_BOUNDS_CHECK)
     unsigned int v = 0;
+    if (getenv("PRL_BOUNDS_SELFTEST")) bounds_selftest_kernel<<<1, 32>>>(64);
     if (cudaDeviceSynchronize() != cudaSuccess) return -2;
     if (cudaMemcpyFromSymbol(&v, g_prl_bounds_violations, sizeof v) != cudaSuccess) return -2;
     return (int32_t)v;
@@ -512,7 +517,8 @@ int prl_batch_sync(prl_batch* b) {
     CUDA_TRY(cudaMemcpyAsync(&flag, b->overflow, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
     CUDA_TRY(cudaStreamSynchronize(b->stream));
     if (flag) {
-        set_error("an environment needed more than PRL_MAX_CONTACTS=%d simultaneous contact manifolds; its trajectory is no longer exact", PRL_MAX_CONTACTS);
+        set_error("an environment needed more simultaneous contact manifolds than the kernels hold (%d); its trajectory is no longer exact",
+                  (b->host_world.n_bodies > 1 && b->host_world.n_pairs > MAXC) ? MAXC_WIDE : MAXC);
         return PRL_ERR_OVERFLOW;
     }
     return PRL_OK;

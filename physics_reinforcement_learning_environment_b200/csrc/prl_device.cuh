@@ -514,9 +514,17 @@ struct Contacts {
     // sc[s]: its solver contacts (world space), refreshed whenever the narrow phase visits the pair
     //   [0] = (normal.x, normal.y, pt0.x, pt0.y)   [1] = (dist0, pt1.x, pt1.y, dist1)
     f4 sc[S][2];
+    // S > 16 ("wide": worlds with pushable blocks and more than 16 candidate pairs): the sorted manifold
+    // list, the slot -> pair table, the step's constraint list and the narrow-phase candidates no longer
+    // fit 64-bit registers as nibbles / bytes and live here, one byte per entry
+    uint8_t order[S > 16 ? S : 1], spair[S > 16 ? S : 1], cons[S > 16 ? S : 1], cand[S > 16 ? S : 1];
 };
 
 struct alignas(8) f2 { float x, y; };
+
+// manifold slots per environment: MAXC, or twice that ("wide" lists in thread-local bytes, Stepper::kWide)
+// for worlds with pushable blocks and more candidate pairs than the slot == pair tables hold
+template <int NB, class WT> struct SlotsOf { static constexpr int value = (NB > 1 && WT::kMaxPairs > MAXC) ? MAXC_WIDE : MAXC; };
 
 template <int NB, int S, class WT = DevWorld, int CAP = 8>
 struct Stepper {
@@ -606,9 +614,28 @@ struct Stepper {
     // slot == pair index for worlds with at most S candidate pairs (the shipped levels): the live
     // manifolds are a bit mask, and selection / broad phase are mask algebra
     static constexpr bool kDirect = WT::kMaxPairs <= S;
-    PRL_D int slot_at(int k) const { return (int)((e.order >> (4 * k)) & 15u); }
+    static constexpr int kSlots = S;
+    static constexpr bool kWide = S > 16;  // lists in thread-local bytes instead of register nibbles
+    static_assert(S <= 32, "the slot masks are 32 bits wide");
+    PRL_D int slot_at(int i) const { return kWide ? (int)k.order[i] : (int)((e.order >> (4 * i)) & 15u); }
     PRL_D int pair_of(int slot) const {
-        return kDirect ? slot : (int)(((slot < 8 ? e.spair[0] : e.spair[1]) >> (8 * (slot & 7))) & 0xffu);
+        if (kDirect) return slot;
+        if (kWide) return (int)k.spair[slot];
+        return (int)(((slot < 8 ? e.spair[0] : e.spair[1]) >> (8 * (slot & 7))) & 0xffu);
+    }
+    PRL_D void set_pair(int slot, int pair) {
+        if (kDirect) return;
+        if (kWide) { k.spair[slot] = (uint8_t)pair; return; }
+        uint64_t sh = 8 * (slot & 7);
+        if (slot < 8) e.spair[0] = (e.spair[0] & ~(0xffull << sh)) | ((uint64_t)pair << sh);
+        else e.spair[1] = (e.spair[1] & ~(0xffull << sh)) | ((uint64_t)pair << sh);
+    }
+    // the step's constraints (slots, two-body first) and the narrow-phase candidates (pair indices)
+    PRL_D int cons_at(int i) const { return kWide ? (int)k.cons[i] : (int)((cons >> (4 * i)) & 15u); }
+    PRL_D void cons_push(int slot) {
+        if (kWide) k.cons[ncons] = (uint8_t)slot;
+        else cons |= (uint64_t)slot << (4 * ncons);
+        ++ncons;
     }
     // iteration over the live manifolds in ascending pair order: for (it = it_begin(); it_ok(it); it = it_next(it))
     PRL_D int it_begin() const { return kDirect ? first_bit_from(e.used, 0) : 0; }
@@ -696,11 +723,7 @@ struct Stepper {
         f4 a, b, c, d;
         a.x = bits_f32((uint32_t)pair | ((uint32_t)m.npts << 8));
         set_ns(slot, ns);
-        if (!kDirect) {
-            uint64_t sh = 8 * (slot & 7);
-            if (slot < 8) e.spair[0] = (e.spair[0] & ~(0xffull << sh)) | ((uint64_t)pair << sh);
-            else e.spair[1] = (e.spair[1] & ~(0xffull << sh)) | ((uint64_t)pair << sh);
-        }
+        set_pair(slot, pair);
         a.y = m.n1.x; a.z = m.n1.y; a.w = m.n2.x;
         b.x = m.n2.y; b.y = m.p1[0].x; b.z = m.p1[0].y; b.w = m.p2[0].x;
         c.x = m.p2[0].y; c.y = m.dist[0]; c.z = m.p1[1].x; c.w = m.p1[1].y;
@@ -724,21 +747,32 @@ struct Stepper {
             store_manifold(slot, p, m, collider_pose(W.pair_c1[p]));
         }
     }
-    PRL_D void remove_at(int k) {
-        int slot = slot_at(k);
+    PRL_D void remove_at(int i) {
+        int slot = slot_at(i);
         e.used &= ~(1u << slot);
-        uint64_t low = k == 0 ? 0ull : (e.order & (~0ull >> (64 - 4 * k)));
-        uint64_t high = k >= 15 ? 0ull : (e.order >> (4 * (k + 1))) << (4 * k);
-        e.order = low | high;
+        if (kWide) {
+#pragma unroll 1
+            for (int j = i; j + 1 < e.count; ++j) k.order[j] = k.order[j + 1];
+        } else {
+            uint64_t low = i == 0 ? 0ull : (e.order & (~0ull >> (64 - 4 * i)));
+            uint64_t high = i >= 15 ? 0ull : (e.order >> (4 * (i + 1))) << (4 * i);
+            e.order = low | high;
+        }
         --e.count;
     }
-    // allocate a slot and link it at sorted position k; -1 on overflow
-    PRL_D int insert_at(int k) {
+    // allocate a slot and link it at sorted position i; -1 on overflow
+    PRL_D int insert_at(int i) {
         int slot = first_zero_bit(e.used);
         if (slot >= S) { e.flags |= FLAG_OVERFLOW; return -1; }
-        uint64_t low = k == 0 ? 0ull : (e.order & (~0ull >> (64 - 4 * k)));
-        uint64_t high = k == 0 ? e.order : (e.order >> (4 * k));
-        e.order = low | ((uint64_t)slot << (4 * k)) | (k >= 15 ? 0ull : (high << (4 * (k + 1))));
+        if (kWide) {
+#pragma unroll 1
+            for (int j = e.count; j > i; --j) k.order[j] = k.order[j - 1];
+            k.order[i] = (uint8_t)slot;
+        } else {
+            uint64_t low = i == 0 ? 0ull : (e.order & (~0ull >> (64 - 4 * i)));
+            uint64_t high = i == 0 ? e.order : (e.order >> (4 * i));
+            e.order = low | ((uint64_t)slot << (4 * i)) | (i >= 15 ? 0ull : (high << (4 * (i + 1))));
+        }
         e.used |= 1u << slot;
         ++e.count;
         return slot;
@@ -1205,8 +1239,7 @@ struct Stepper {
                 bool awake1 = h1 >= 0 && ((active >> h1) & 1u);
                 bool awake2 = h2 >= 0 && ((active >> h2) & 1u);
                 if (!awake1 && !awake2) continue;
-                cons |= (uint64_t)slot << (4 * ncons);
-                ++ncons;
+                cons_push(slot);
                 need += ns;
                 if (two_body) ntb += ns;
                 else if (p < W.n_player_pairs) nplayer += ns;
@@ -1237,12 +1270,12 @@ struct Stepper {
             }
         } else {
             f4 n0 = {}, n1 = {};
-            if (ncons > 0) { const int s0_ = (int)(cons & 15u); n0 = k.sc[s0_][0]; n1 = k.sc[s0_][1]; }
+            if (ncons > 0) { const int s0_ = cons_at(0); n0 = k.sc[s0_][0]; n1 = k.sc[s0_][1]; }
 #pragma unroll 1
             for (int i = 0; i < ncons; ++i) {
                 const f4 c0 = n0, c1 = n1;
-                nrows = generate_constraint((int)((cons >> (4 * i)) & 15u), nrows, c0, c1);
-                if (i + 1 < ncons) { const int sn = (int)((cons >> (4 * (i + 1))) & 15u); n0 = k.sc[sn][0]; n1 = k.sc[sn][1]; }
+                nrows = generate_constraint(cons_at(i), nrows, c0, c1);
+                if (i + 1 < ncons) { const int sn = cons_at(i + 1); n0 = k.sc[sn][0]; n1 = k.sc[sn][1]; }
             }
         }
         PRL_TICK(5);
@@ -1452,8 +1485,9 @@ struct Stepper {
                 }
                 if (have) ++k;
                 if (modified && ov) {
-                    if (ncand < 16) {
-                        if (ncand < 8) cand[0] |= (uint64_t)p << (8 * ncand);
+                    if (ncand < S) {
+                        if (kWide) this->k.cand[ncand] = (uint8_t)p;
+                        else if (ncand < 8) cand[0] |= (uint64_t)p << (8 * ncand);
                         else cand[1] |= (uint64_t)p << (8 * (ncand - 8));
                         ++ncand;
                     }
@@ -1491,7 +1525,7 @@ struct Stepper {
         // lockstep. Player pairs (capsule-cuboid) sort first, block pairs (cuboid-cuboid) after.
         int k = 0;
         int i = 0;
-        auto cand_at = [&](int q) { return (int)(((q < 8 ? cand[0] : cand[1]) >> (8 * (q & 7))) & 0xffu); };
+        auto cand_at = [&](int q) { return kWide ? (int)this->k.cand[q] : (int)(((q < 8 ? cand[0] : cand[1]) >> (8 * (q & 7))) & 0xffu); };
 #pragma unroll 1
         for (; i < ncand && cand_at(i) < W.n_player_pairs; ++i) {
             int p = cand_at(i);

@@ -43,7 +43,7 @@ constexpr int kWarpBlock = 32;  // rollouts of populations too small to fill the
 // (kernels of 64- and 32-thread blocks have no block barrier, so a round only costs the warp that
 // needs it: they keep 7-row columns, which lets seven 64-thread blocks share an SM)
 template <int NB, int BLOCK> struct RowCap { static constexpr int value = NB == 1 ? 4 : (NB == 2 ? (BLOCK > 64 ? PRL_ROWCAP2 : 7) : 8); };
-template <int NB, class WT, int BLOCK = 64> using SimOf = Stepper<NB, MAXC, WT, RowCap<NB, BLOCK>::value>;
+template <int NB, class WT, int BLOCK = 64> using SimOf = Stepper<NB, SlotsOf<NB, WT>::value, WT, RowCap<NB, BLOCK>::value>;
 // Rollouts of large batches run ONE block of 448 threads per SM (the same 14 warps, 148 x 448 >=
 // 65536) with a block barrier at the top of every step: the step is ~4000 straight-line
 // instructions outside the solver's loops, and warps of one SM that are in the same phase of the
@@ -129,8 +129,8 @@ __device__ __forceinline__ void stage_world(WT* dst, const DevWorld* __restrict_
     __syncthreads();
 }
 
-template <int NB, class WT>
-__device__ __forceinline__ void env_init(const WT& W, Env<NB>& e) {
+template <int NB, class WT, int S>
+__device__ __forceinline__ void env_init(const WT& W, Env<NB, S>& e) {
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
         int c = b < W.n_bodies ? W.collider_of[b] : 0;
@@ -148,8 +148,8 @@ __device__ __forceinline__ void env_init(const WT& W, Env<NB>& e) {
     e.ns1 = e.ns2 = 0;
 }
 
-template <int NB, class WT>
-__device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct, const uint32_t* __restrict__ st, int64_t n, int64_t i) {
+template <int NB, class WT, int S>
+__device__ __forceinline__ void env_load(const WT& W, Env<NB, S>& e, Contacts<S>& ct, const uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto ld = [&](int f) { return __uint_as_float(st[(int64_t)f * n + i]); };
     uint32_t fl = st[(int64_t)F_FLAGS * n + i];
     e.sleeping = fl & 0xffu;
@@ -175,7 +175,8 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct
     int base = F_DYN + 8 * (W.n_bodies - 1);
     const int count = e.count;
     e.order = 0xfedcba9876543210ull;
-    e.used = direct ? 0u : (1u << count) - 1u;
+    if (S > 16) for (int q = 0; q < S; ++q) ct.order[q] = (uint8_t)q;  // wide lists: HBM slot k = manifold k = record k
+    e.used = direct ? 0u : (count >= 32 ? ~0u : (1u << count) - 1u);
     e.spair[0] = e.spair[1] = 0;
     e.ns1 = e.ns2 = 0;
     // all 15 words of a slot are requested before the first one is used:
@@ -189,7 +190,7 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct
         for (int j = 0; j < MF_WORDS; ++j) w[j] = st[(int64_t)(f + j) * n + i];
         const uint32_t h = w[0];
         int slot = direct ? (int)(h & 0xffu) : k;
-        PRL_CHECK(slot >= 0 && slot < MAXC, 2);
+        PRL_CHECK(slot >= 0 && slot < S, 2);
         if (direct) e.used |= 1u << slot;
         f4* rec = ct.mf[slot];
         f4 q;
@@ -200,8 +201,8 @@ __device__ __forceinline__ void env_load(const WT& W, Env<NB>& e, Contacts<>& ct
     }
 }
 
-template <int NB, class WT>
-__device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, const Contacts<>& ct, uint32_t* __restrict__ st, int64_t n, int64_t i) {
+template <int NB, class WT, int S>
+__device__ __forceinline__ void env_store(const WT& W, const Env<NB, S>& e, const Contacts<S>& ct, uint32_t* __restrict__ st, int64_t n, int64_t i) {
     auto sf = [&](int f, float v) { st[(int64_t)f * n + i] = __float_as_uint(v); };
     constexpr bool direct = SimOf<NB, WT>::kDirect;
     int count = direct ? __popc(e.used) : e.count;
@@ -221,8 +222,8 @@ __device__ __forceinline__ void env_store(const WT& W, const Env<NB>& e, const C
     uint32_t left = e.used;
 #pragma unroll 1
     for (int k = 0; k < count; ++k) {
-        int slot = direct ? __ffs((int)left) - 1 : (int)((e.order >> (4 * k)) & 15u);
-        PRL_CHECK(k < W.n_slots && slot >= 0 && slot < MAXC, 4);
+        int slot = direct ? __ffs((int)left) - 1 : (S > 16 ? (int)ct.order[k] : (int)((e.order >> (4 * k)) & 15u));
+        PRL_CHECK(k < W.n_slots && slot >= 0 && slot < S, 4);
         left &= left - 1;
         int f = base + MF_WORDS * k;
         const f4* rec = ct.mf[slot];
@@ -270,8 +271,8 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) step_kernel(const DevW
     // lanes past the end replay the last environment and skip the stores
     const bool live = i < n;
     if (!live) i = n - 1;
-    Env<NB> e;
-    Contacts<> ct;
+    typename Sim::E e;
+    Contacts<Sim::kSlots> ct;
     env_load(W, e, ct, st, n, i);
     float score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
     int win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
@@ -321,8 +322,8 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     int64_t i = BLOCK == kWarpBlock ? (int64_t)blockIdx.x * lanes + threadIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool live = i < n && (BLOCK != kWarpBlock || (int)threadIdx.x < lanes);
     if (!live) i = n - 1;  // pad lanes only take part in the warp's votes and the block's barriers
-    Env<NB> e;
-    Contacts<> ct;
+    typename Sim::E e;
+    Contacts<Sim::kSlots> ct;
     env_init(W, e);
     Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     // running minimum of the SQUARED physics-space distance to the goals (Stepper::finish_step_sq):
@@ -485,8 +486,8 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) policy_rollout_kernel(
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     if (!live) i = n - 1;
-    Env<NB> e;
-    Contacts<> ct;
+    typename Sim::E e;
+    Contacts<Sim::kSlots> ct;
     env_init(W, e);
     Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     float score = __int_as_float(0x7f800000);
@@ -534,8 +535,8 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) observation_kernel(con
     stage_world(&W, dw);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Env<NB> e;
-    Contacts<> ct;
+    typename Sim::E e;
+    Contacts<Sim::kSlots> ct;
     env_load(W, e, ct, st, n, i);
     Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     sim.refresh_solver_contacts();
@@ -561,8 +562,8 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) trajectory_kernel(cons
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < n;
     if (!live) i = n - 1;
-    Env<NB> e;
-    Contacts<> ct;
+    typename Sim::E e;
+    Contacts<Sim::kSlots> ct;
     env_init(W, e);
     Sim sim(W, e, ct, row_pool + (threadIdx.x >> 5) * Sim::kWarpBytes);
     const uint8_t* genome = genomes + i * (int64_t)genome_len;

@@ -219,7 +219,11 @@ int build_dev_world(prl_world* w) {
             }
         }
     }
-    d.n_slots = np < MAXC ? np : MAXC;
+    {
+        // manifold slots kept per environment in HBM: as many as the kernel variant holds live at once
+        const int cap = (d.n_bodies > 1 && np > MAXC) ? MAXC_WIDE : MAXC;
+        d.n_slots = np < cap ? np : cap;
+    }
     return PRL_OK;
 }
 

@@ -19,6 +19,7 @@ constexpr int MIDB = 5;                      // kernels keep the bodies in regis
 constexpr int MAXP = PRL_MAX_PAIRS;
 constexpr int MAXG = PRL_MAX_GOALS;
 constexpr int MAXC = PRL_MAX_CONTACTS;       // manifold slots per environment
+constexpr int MAXC_WIDE = 2 * MAXC;          // ... in worlds with pushable blocks and more than MAXC candidate pairs
 constexpr int MF_WORDS = 15;                 // HBM words per manifold slot (see prl_device.cuh)
 
 // MC / MP / MG: collider, pair and goal capacity. The host always builds the full-size DevWorld;

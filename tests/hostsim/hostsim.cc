@@ -38,8 +38,8 @@ template <class SIM> static void count_need(const SIM& sim) {
 // rows per column of the solver's row storage (4 or 8): the layout must not change any result
 extern "C" void hs_set_row_cap(int cap) { g_row_cap = cap <= 4 ? 4 : 8; }
 
-template <int NB, class WT>
-static void init_env(const WT& W, Env<NB>& e) {
+template <int NB, class WT, int S>
+static void init_env(const WT& W, Env<NB, S>& e) {
     memset(&e, 0, sizeof e);
     for (int b = 0; b < NB; ++b) {
         int c = b < W.n_bodies ? W.collider_of[b] : 0;
@@ -51,11 +51,11 @@ static void init_env(const WT& W, Env<NB>& e) {
 template <int NB, int PR, class WT>
 static float rollout(const WT& W, const uint8_t* genome, int genome_len, int repeat_move, int number_of_steps,
                      int early_exit, float* traj, int* win_out, int* steps_out, int* overflow) {
-    static Env<NB> e;
-    static Contacts<> k;
+    using Sim = Stepper<NB, SlotsOf<NB, WT>::value, WT, PR>;
+    static typename Sim::E e;
+    static Contacts<Sim::kSlots> k;
     init_env(W, e);
     memset(&k, 0, sizeof k);
-    using Sim = Stepper<NB, MAXC, WT, PR>;
     alignas(16) static unsigned char pool[Sim::kWarpBytes + Sim::kPoolPad];
     Sim sim(W, e, k, pool);
     float qmin = INFINITY;
@@ -104,11 +104,11 @@ static float rollout(const WT& W, const uint8_t* genome, int genome_len, int rep
 template <int NB, int PR, class WT>
 static float policy_rollout(const WT& W, const float* theta, long stride, int hidden, int number_of_steps, int early_exit,
                             float* obs_out, int* win_out, int* steps_out, int* overflow) {
-    static Env<NB> e;
-    static Contacts<> k;
+    using Sim = Stepper<NB, SlotsOf<NB, WT>::value, WT, PR>;
+    static typename Sim::E e;
+    static Contacts<Sim::kSlots> k;
     init_env(W, e);
     memset(&k, 0, sizeof k);
-    using Sim = Stepper<NB, MAXC, WT, PR>;
     alignas(16) static unsigned char pool[Sim::kWarpBytes + Sim::kPoolPad];
     Sim sim(W, e, k, pool);
     float score = INFINITY;
@@ -185,9 +185,9 @@ extern "C" int hs_rollout(const char* json, size_t len, const uint8_t* genome, i
     } else if (W.n_bodies == 1) {
         *score = small_pool ? rollout<1, 4>(W, HS_ARGS) : rollout<1, 8>(W, HS_ARGS);
     } else if (W.n_bodies <= MIDB) {
-        *score = small_pool ? rollout<MIDB, 4>(W, HS_ARGS) : rollout<MIDB, 8>(W, HS_ARGS);
+        *score = rollout<MIDB, 8>(W, HS_ARGS);  // (32 manifold slots = up to 64 rows: 8-row columns, as the kernels)
     } else {
-        *score = small_pool ? rollout<MAXB, 4>(W, HS_ARGS) : rollout<MAXB, 8>(W, HS_ARGS);
+        *score = rollout<MAXB, 8>(W, HS_ARGS);
     }
 #undef HS_ARGS
     return 0;

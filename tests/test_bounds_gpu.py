@@ -62,6 +62,16 @@ def test_no_index_leaves_its_array_in_the_bounds_checked_build():
     assert "BOUNDS 0" in out.stdout, out.stdout[-500:]
 
 
+def test_a_failed_check_is_recorded():
+    """Negative control: with PRL_BOUNDS_SELFTEST the debug library runs a check that must fail (code 30)."""
+    debug = os.path.join(ROOT, "physics_reinforcement_learning_environment_b200", "libprl_debug.so")
+    env = dict(os.environ, PRL_LIBRARY=debug, PRL_ROOT=ROOT, PRL_BOUNDS_SELFTEST="1")
+    code = ("import os, sys; sys.path.insert(0, os.environ['PRL_ROOT']);"
+            "from physics_reinforcement_learning_environment_b200 import _lib; print('BOUNDS', _lib.lib().prl_debug_bounds_violations())")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert f"BOUNDS {1 << 30}" in out.stdout, out.stdout + out.stderr[-2000:]
+
+
 def test_the_product_library_has_no_checks():
     from physics_reinforcement_learning_environment_b200 import _lib
     assert _lib.lib().prl_debug_bounds_violations() == -1

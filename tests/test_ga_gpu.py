@@ -154,8 +154,8 @@ def test_ga_reports_contact_overflow_instead_of_selecting_on_inexact_scores():
     """A world whose environments need more simultaneous contact manifolds than PRL_MAX_CONTACTS:
     the scores are not exact, so prl_ga_best must fail with PRL_ERR_OVERFLOW rather than report a
     best agent (the batch API reports the same through prl_batch_sync)."""
-    # a long plank resting on 20 posts: 20 plank-post manifolds alive at once
-    n_posts = 20
+    # a long plank resting on 40 posts: 40 plank-post manifolds alive at once (the kernels hold 32)
+    n_posts = 40
     objs = [{"object": {"Block": {"fixed": True}}, "position": [-300.0 + 30.0 * i, -40.0, float(i + 1)], "scale": [14.0, 40.0], "rotation": 0.0}
             for i in range(n_posts)]
     objs.append({"object": {"Block": {"fixed": False}}, "position": [-15.0, -14.0, 30.0], "scale": [30.0 * n_posts + 20.0, 12.0], "rotation": 0.0})

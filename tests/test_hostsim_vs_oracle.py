@@ -60,7 +60,7 @@ def test_trajectories_bit_exact(name):
         assert np.array_equal(t.view(np.uint32), o.view(np.uint32))
 
 
-@pytest.mark.parametrize("n_posts", [6, 8])
+@pytest.mark.parametrize("n_posts", [6, 8, 20])
 def test_many_constraint_rows(n_posts):
     """12-18 constraint rows per environment (a plank on many posts)."""
     world = many_supports_world(n_posts)

@@ -113,7 +113,7 @@ def test_two_pushable_blocks_rotations_negative_scales():
         assert np.array_equal(bits(st[i]), bits(o.state()))
 
 
-@pytest.mark.parametrize("n_posts", [6, 8])
+@pytest.mark.parametrize("n_posts", [6, 8, 20])
 def test_more_rows_than_a_column_holds_solves_in_rounds(n_posts):
     """A plank on many posts needs 12-18 constraint rows per environment: more than a column of
     the warp's row storage, so the lanes of a warp take turns (two / four rounds). Rollouts and
