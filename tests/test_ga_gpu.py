@@ -158,7 +158,7 @@ def test_ga_reports_contact_overflow_instead_of_selecting_on_inexact_scores():
     n_posts = 40
     objs = [{"object": {"Block": {"fixed": True}}, "position": [-300.0 + 30.0 * i, -40.0, float(i + 1)], "scale": [14.0, 40.0], "rotation": 0.0}
             for i in range(n_posts)]
-    objs.append({"object": {"Block": {"fixed": False}}, "position": [-15.0, -14.0, 30.0], "scale": [30.0 * n_posts + 20.0, 12.0], "rotation": 0.0})
+    objs.append({"object": {"Block": {"fixed": False}}, "position": [-300.0 + 15.0 * (n_posts - 1), -14.0, 50.0], "scale": [30.0 * n_posts + 20.0, 12.0], "rotation": 0.0})
     objs.append({"object": "Goal", "position": [500.0, 30.0, 31.0], "scale": [60.0, 60.0], "rotation": 0.0})
     world = prl.World.from_json(json.dumps({"player_position": [0.0, 24.0], "objects": objs}))
     env = prl.BatchedEnvironment(world, 8)
