@@ -60,11 +60,11 @@ constexpr int kBigBlock = 448;
 #endif
 constexpr int kRegroupEvery = PRL_REGROUP_EVERY;
 constexpr int kRegroupKeys = 34;  // 0 = finished, 1 + min(rows, 32)
-constexpr size_t kRegroupBytes = (kRegroupKeys + 2 * kBigBlock) * sizeof(int);
+template <int BLOCK> constexpr size_t regroup_bytes() { return BLOCK >= kBigBlock ? (kRegroupKeys + 2 * BLOCK) * sizeof(int) : 0; }
 template <int NB, class WT, int BLOCK>
 constexpr size_t rollout_smem_bytes() {
     return ((sizeof(WT) + 15) / 16) * 16 + (size_t)(BLOCK / 32) * SimOf<NB, WT, BLOCK>::kWarpBytes + SimOf<NB, WT, BLOCK>::kPoolPad +
-           (BLOCK == kBigBlock ? kRegroupBytes : 0);
+           regroup_bytes<BLOCK>();
 }
 
 // One step's solve for the lanes of a warp. The warp first agrees on the shape of its row
@@ -305,11 +305,11 @@ __global__ void __launch_bounds__(kBlock, NB > 2 ? 6 : 7) step_kernel(const DevW
 // distance_to_goals. early_exit reproduces the reference's break-on-win (including the tail's
 // extra step after a win); without it every step is executed (throughput runs).
 template <int NB, class WT, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 7)) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
+__global__ void __launch_bounds__(BLOCK, BLOCK >= kBigBlock ? 1 : (NB > 2 ? 6 : 7)) rollout_kernel(const DevWorld* __restrict__ dw, uint32_t* __restrict__ st, int64_t n,
                                                          const uint8_t* __restrict__ genomes, int genome_len, int repeat_move,
                                                          int number_of_steps, int early_exit,
                                                          float* __restrict__ out_score, int32_t* __restrict__ out_win,
-                                                         int* __restrict__ overflow, int lanes) {
+                                                         int* __restrict__ overflow, int lanes, int per_block) {
     using Sim = SimOf<NB, WT, BLOCK>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WT& W = *reinterpret_cast<WT*>(smem_raw);
@@ -319,8 +319,12 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     // SPARSE warps: a rollout of few environments is bound by the latency of a warp's step, and a warp
     // executes the union of its lanes' paths -- with 7 environments instead of 32 most steps of a random
     // population are pure free flight, and four such warps per SM overlap their latencies.
-    int64_t i = BLOCK == kWarpBlock ? (int64_t)blockIdx.x * lanes + threadIdx.x : (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i < n && (BLOCK != kWarpBlock || (int)threadIdx.x < lanes);
+    // General mapping: a block owns the `per_block` environments [blockIdx * per_block, ...), warp w of it the
+    // `lanes` environments [w * lanes, ...) of those (dense: per_block = BLOCK, lanes = 32).
+    const int lane_ = (int)(threadIdx.x & 31u), warp_ = (int)(threadIdx.x >> 5);
+    int local = warp_ * lanes + lane_;
+    int64_t i = (int64_t)blockIdx.x * per_block + local;
+    bool live = lane_ < lanes && local < per_block && i < n;
     if (!live) i = n - 1;  // pad lanes only take part in the warp's votes and the block's barriers
     typename Sim::E e;
     Contacts<Sim::kSlots> ct;
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
     const int total = main_steps + number_of_steps % repeat_move;
     int g = 0, rep = 0, t = live ? 0 : total, iter = 0;
     uint32_t gene = genome_len > 0 ? (genome[0] & 7u) : 0u;
-    int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes + Sim::kPoolPad);  // only if BLOCK == kBigBlock
+    int* regroup = reinterpret_cast<int*>(row_pool + (BLOCK / 32) * Sim::kWarpBytes + Sim::kPoolPad);  // only if BLOCK >= kBigBlock
 #if defined(PRL_PHASE_TIMING)
     sim.tlast = clock64();
 #endif
@@ -389,11 +393,11 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
 #endif
         // (single-body worlds in SM-wide blocks run in lock step but are not regrouped: sorting the few
         // walking players of a population into their own warps does not shorten those warps' chains)
-        if (BLOCK == kBigBlock && NB > 1 && PRL_UNLIKELY(iter > 0 && iter % kRegroupEvery == 0)) {
+        if (BLOCK >= kBigBlock && NB > 1 && PRL_UNLIKELY(iter > 0 && iter % kRegroupEvery == 0)) {
             // ---- regroup: park, sort, pick up (all threads of the block are here, nothing pending)
             int* hist = regroup;
             int* perm_env = regroup + kRegroupKeys;
-            int* perm_live = perm_env + kBigBlock;
+            int* perm_live = perm_env + BLOCK;
             if (live) {
                 env_store(W, e, ct, st, n, i);
                 st[(int64_t)F_SCORE * n + i] = __float_as_uint(score);
@@ -408,12 +412,16 @@ __global__ void __launch_bounds__(BLOCK, BLOCK == kBigBlock ? 1 : (NB > 2 ? 6 : 
             __syncthreads();
             int off = 0;
             for (int k = key + 1; k < kRegroupKeys; ++k) off += hist[k];
-            PRL_CHECK(off + pos >= 0 && off + pos < kBigBlock && key >= 0 && key < kRegroupKeys, 6);
-            perm_env[off + pos] = (int)(i - (int64_t)blockIdx.x * BLOCK);
+            PRL_CHECK(off + pos >= 0 && off + pos < BLOCK && key >= 0 && key < kRegroupKeys, 6);
+            perm_env[off + pos] = live ? (int)(i - (int64_t)blockIdx.x * per_block) : -1;
             perm_live[off + pos] = live ? 1 : 0;
             __syncthreads();
-            i = (int64_t)blockIdx.x * BLOCK + perm_env[threadIdx.x];
-            live = perm_live[threadIdx.x] != 0;
+            // running rollouts sort first: the warps' real lanes take them in order, pad lanes take the rest
+            const int slots = (BLOCK / 32) * lanes;
+            const int mine = lane_ < lanes ? warp_ * lanes + lane_ : slots + warp_ * (32 - lanes) + (lane_ - lanes);
+            PRL_CHECK(mine >= 0 && mine < BLOCK, 6);
+            live = perm_live[mine] != 0;
+            i = live ? (int64_t)blockIdx.x * per_block + perm_env[mine] : n - 1;
             env_load(W, e, ct, st, n, i);
             score = __uint_as_float(st[(int64_t)F_SCORE * n + i]);
             win_step = (int)st[(int64_t)F_WIN_STEP * n + i];
