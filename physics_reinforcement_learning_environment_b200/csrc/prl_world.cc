@@ -493,23 +493,45 @@ int parse_world_json(const char* s, size_t len, prl_world* out) {
     return PRL_ERR_PARSE;
 }
 
-// serde_json prints f32 with ryu: shortest round-trip digits, always a '.0' on integers,
-// exponents as e-7 / e20
+// serde_json prints f32 with ryu (ryu::Buffer::format_finite -> pretty::format32): the shortest digits
+// that round-trip, laid out by decimal exponent. With `length` digits d1 d2 ... and value
+// digits * 10^k, kk = length + k:
+//   0 <= k  and kk <= 13   ->  digits, k zeros, ".0"            (1234e7  -> 12340000000.0)
+//   0 <  kk <= 13          ->  point inside the digits           (1234e-2 -> 12.34)
+//   -6 < kk <= 0           ->  "0.", -kk zeros, digits           (1234e-7 -> 0.0001234)
+//   otherwise              ->  d1[.d2...]e<kk-1>                 (1e30, 1.234e-7)
+// Non-finite values are written as `null` (serde_json's serialize_f32).
 static void put_f32(std::string& s, float v) {
+    if (!std::isfinite(v)) { s += "null"; return; }
+    if (std::signbit(v)) s += '-';
+    if (v == 0.0f) { s += "0.0"; return; }
     char buf[64];
-    auto r = std::to_chars(buf, buf + sizeof buf, v);
+    auto r = std::to_chars(buf, buf + sizeof buf, std::fabs(v), std::chars_format::scientific);  // shortest round-trip digits
     std::string t(buf, r.ptr);
-    size_t ep = t.find('e');
-    if (ep != std::string::npos) {
-        std::string mant = t.substr(0, ep), ex = t.substr(ep + 1);
-        bool neg = !ex.empty() && ex[0] == '-';
-        if (!ex.empty() && (ex[0] == '-' || ex[0] == '+')) ex.erase(0, 1);
-        while (ex.size() > 1 && ex[0] == '0') ex.erase(0, 1);
-        t = mant + "e" + (neg ? "-" : "") + ex;
-    } else if (t.find('.') == std::string::npos && t.find("inf") == std::string::npos && t.find("nan") == std::string::npos) {
-        t += ".0";
+    const size_t ep = t.find('e');
+    std::string digits;
+    for (char ch : t.substr(0, ep)) if (ch != '.') digits += ch;
+    const int exp10 = atoi(t.c_str() + ep + 1);  // of the first digit
+    const int length = (int)digits.size();
+    const int kk = exp10 + 1, k = kk - length;
+    if (0 <= k && kk <= 13) {
+        s += digits;
+        s.append((size_t)k, '0');
+        s += ".0";
+    } else if (0 < kk && kk <= 13) {
+        s += digits.substr(0, (size_t)kk);
+        s += '.';
+        s += digits.substr((size_t)kk);
+    } else if (-6 < kk && kk <= 0) {
+        s += "0.";
+        s.append((size_t)(-kk), '0');
+        s += digits;
+    } else {
+        s += digits[0];
+        if (length > 1) { s += '.'; s += digits.substr(1); }
+        s += 'e';
+        s += std::to_string(kk - 1);
     }
-    s += t;
 }
 
 std::string world_to_json(const prl_world* w) {

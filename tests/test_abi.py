@@ -170,3 +170,48 @@ def test_no_cpu_fallback():
     with pytest.raises(prl.PrlError) as e:
         prl.BatchedEnvironment(w, 8)
     assert e.value.status == _lib.PRL_ERR_CUDA
+
+
+def ryu_f32(x):
+    """serde_json / ryu::pretty::format32 restated on numpy's shortest round-trip digits."""
+    x = np.float32(x)
+    if not np.isfinite(x):
+        return "null"
+    sign = "-" if np.signbit(x) else ""
+    if x == 0:
+        return sign + "0.0"
+    sci = np.format_float_scientific(abs(x), unique=True, trim="-")   # e.g. '1.234e-07', '1e+30'
+    mant, exp = sci.split("e")
+    digits = mant.replace(".", "")
+    kk = int(exp) + 1
+    k = kk - len(digits)
+    if 0 <= k and kk <= 13:
+        return sign + digits + "0" * k + ".0"
+    if 0 < kk <= 13:
+        return sign + digits[:kk] + "." + digits[kk:]
+    if -6 < kk <= 0:
+        return sign + "0." + "0" * (-kk) + digits
+    return sign + digits[0] + ("." + digits[1:] if len(digits) > 1 else "") + "e" + str(kk - 1)
+
+
+def test_f32_formatting_follows_ryu():
+    """serde_json::to_string writes f32 with ryu: known spellings, the layout thresholds (13 integer digits,
+    five leading zeros), and 20000 random bit patterns that must also parse back to the same bits."""
+    known = {1.0: "1.0", -0.0: "-0.0", 0.5: "0.5", 1e12: "1000000000000.0", 1e13: "1e13", 123456.79: "123456.79",
+             1e-5: "0.00001", 1e-6: "0.000001", 1e-7: "1e-7", 1.234e-7: "1.234e-7", 3.4028235e38: "3.4028235e38",
+             1e-45: "1e-45", 16777216.0: "16777216.0", 0.1: "0.1", 1234.5: "1234.5"}
+    rng = np.random.Generator(np.random.Philox(2024))
+    bits = rng.integers(0, 2**32, size=20000, dtype=np.uint64).astype(np.uint32)
+    values = [np.float32(v) for v in known] + [b for b in bits.view(np.float32) if np.isfinite(b)]
+    for lo in range(0, len(values), 120):
+        chunk = values[lo:lo + 120]
+        # position[2] is the editor's draw order: stored and written back, ignored by the physics
+        objs = [prl.ObjectAndTransform(prl.WorldObject.block(True), [0.0, 0.0, float(v)], [1.0, 1.0], 0.0) for v in chunk]
+        text = prl.World([0.0, 0.0], objs).to_json()
+        got = [o["position"][2] for o in json.loads(text, parse_float=lambda t: t, parse_int=lambda t: t)["objects"]]
+        for v, g in zip(chunk, got):
+            assert g == ryu_f32(v), (v, g, ryu_f32(v))
+        back = prl.World.from_json(text)
+        assert [np.float32(o.position[2]).view(np.uint32) for o in back.objects] == [np.float32(v).view(np.uint32) for v in chunk]
+    for v, spelled in known.items():
+        assert ryu_f32(v) == spelled, (v, ryu_f32(v), spelled)
