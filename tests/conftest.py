@@ -133,3 +133,21 @@ def random_world(seed):
         z += 1.0
     order = rng.permutation(len(objs))  # object order decides collider / body indices
     return {"player_position": [float(rng.uniform(-100, 100)), float(rng.uniform(20, 90))], "objects": [objs[i] for i in order]}
+
+
+def random_world_many_pushables(seed):
+    """Like random_world but with 4-7 pushable blocks dropped over the floor: piles, body-body contacts,
+    the 8-body kernel variant (5-7 pushables) and the 32-slot manifold lists."""
+    rng = np.random.Generator(np.random.Philox(5000 + seed))
+    objs = [{"object": {"Block": {"fixed": True}}, "position": [300.0, -60.0, 1.0], "scale": [1800.0, 50.0], "rotation": float(rng.uniform(-0.02, 0.02))}]
+    for _ in range(int(rng.integers(0, 5))):
+        objs.append({"object": {"Block": {"fixed": True}}, "position": [float(rng.uniform(-350, 900)), float(rng.uniform(-40, 30)), 2.0],
+                     "scale": [float(rng.uniform(20, 120)), float(rng.uniform(15, 70))],
+                     "rotation": float(rng.uniform(-0.5, 0.5)) if rng.random() < 0.5 else 0.0})
+    for _ in range(int(rng.integers(4, 8))):
+        objs.append({"object": {"Block": {"fixed": False}}, "position": [float(rng.uniform(-200, 500)), float(rng.uniform(-20, 160)), 3.0],
+                     "scale": [float(rng.uniform(25, 120)), float(rng.uniform(12, 50))],
+                     "rotation": float(rng.uniform(-0.4, 0.4)) if rng.random() < 0.5 else 0.0})
+    objs.append({"object": "Goal", "position": [float(rng.uniform(-400, 900)), 20.0, 9.0], "scale": [80.0, 80.0], "rotation": 0.3})
+    order = rng.permutation(len(objs))
+    return {"player_position": [float(rng.uniform(-100, 100)), float(rng.uniform(40, 200))], "objects": [objs[i] for i in order]}

@@ -10,7 +10,8 @@ import pytest
 
 import physics_reinforcement_learning_environment_b200 as prl
 from physics_reinforcement_learning_environment_b200 import _lib
-from conftest import WORLDS, edge_case_worlds, many_supports_world, random_genomes, random_world, synth_world, world_dict, world_text
+from conftest import (WORLDS, edge_case_worlds, many_supports_world, random_genomes, random_world, random_world_many_pushables,
+                      synth_world, world_dict, world_text)
 from oracle import binding as oracle
 from oracle.binding import OracleEnv
 
@@ -419,3 +420,15 @@ def test_policy_rollout_device_buffers_and_edge_world():
     assert np.array_equal(bits(ds.cpu().numpy()), bits(rs)) and np.array_equal(dw.cpu().numpy(), rw)
     with pytest.raises(prl.PrlError):
         env.rollout_policy(params, 33, steps)  # hidden > 32
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_worlds_with_many_pushable_blocks_match_oracle(seed):
+    world = random_world_many_pushables(seed)
+    n, L, repeat, steps = 96, 20, 15, 300
+    genomes = random_genomes(n, L, 700 + seed)
+    env = prl.BatchedEnvironment(prl.World.from_json(json.dumps(world)), n)
+    score, win = env.rollout(genomes, repeat, steps, early_exit=False)
+    env.sync()
+    rs, rw, _ = oracle.rollout_batch(world, genomes, repeat, steps, False, n_threads=os.cpu_count())
+    assert np.array_equal(bits(score), bits(rs)) and np.array_equal(win, rw)
