@@ -304,7 +304,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_env_step": balg,
                          "issue": issue, "kernel_source_sha256": src_hash,
-                         "note": "state stays in registers across the fused horizon, so the kernel is issue-bound, not HBM-bound (DESIGN.md): `issue` is the binding roof"},
+                         "note": "state stays in registers across the fused horizon, so the kernel is not HBM-bound: it is a dependent f32 chain (no FMA) "
+                                 "issued at ~6 cycles per instruction per warp, 14 warps per SM in lock step (DESIGN.md, profiles/r02_experiments.md); "
+                                 "`issue` gives its instruction count and issue-slot utilisation"},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": int(args.envs * genome_len),
                     "d2h_bytes_per_step": int(args.envs * 8)},
